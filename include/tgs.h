@@ -1,0 +1,196 @@
+/*
+ * tgs.h -- torch-free C ABI of the B200-native Touch-GS rasterizer (libtgs.so).
+ *
+ * This is the drop-in boundary of the hot path.  The reference does not
+ * vendor its rasterizer (reference .gitmodules:7-9 -> empty nerfstudio/ submodule), so the
+ * interface each entry point replaces is the *operator* surface the reference's trainer calls
+ * (`ns-train depth-gaussian-splatting`, reference scripts/train_bunny_real.sh:52,
+ * scripts/train_block_data.sh:50), i.e. the public Inria-style C++ entry points
+ * RasterizeGaussiansCUDA / RasterizeGaussiansBackwardCUDA / markVisible named in SURVEY.md
+ * §2.2 rows H2-H10 and §8(b), extended with expected depth, alpha and the fused touch-depth
+ * loss.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 / int32 unless its name ends in
+ *     `_host`;  matrices are 16 floats, passed TRANSPOSED (row-vector convention) exactly as
+ *     the operator's GaussianRasterizationSettings holds them;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - every function returns 0 on success, a negative TGS_E* code or a positive cudaError_t
+ *     otherwise; tgs_last_error() gives the message (thread-local);
+ *   - kernels never own memory: scratch comes from the caller through `tgs_alloc_fn`.
+ */
+#ifndef TGS_H_
+#define TGS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TGS_ABI_VERSION 1
+
+#define TGS_EINVAL   (-1)   /* bad argument combination / shape */
+#define TGS_ENOMEM   (-2)   /* allocator callback returned NULL */
+#define TGS_ESTATE   (-3)   /* saved buffers do not match the call */
+
+/* which scratch buffer an allocation is for (the three opaque byte buffers of SURVEY §8b) */
+#define TGS_BUF_GEOM    0   /* per-Gaussian state, lives fwd -> bwd */
+#define TGS_BUF_BINNING 1   /* per-instance state (sorted list, packed records) */
+#define TGS_BUF_IMAGE   2   /* per-pixel state (final_T, n_contrib, raw depth) */
+#define TGS_BUF_TEMP    3   /* temporaries not needed by backward */
+
+/* Returns a device pointer to >= bytes of memory aligned to >= 256 B, or NULL. */
+typedef void* (*tgs_alloc_fn)(void* user, int which, size_t bytes);
+
+/* depth-loss modes of the fused touch gradient */
+#define TGS_LOSS_NONE 0
+#define TGS_LOSS_L1   1
+#define TGS_LOSS_L2   2
+
+/* Camera + raster settings: mirrors GaussianRasterizationSettings. */
+typedef struct TgsSettings {
+    int32_t image_width;
+    int32_t image_height;
+    float   tanfovx;
+    float   tanfovy;
+    float   scale_modifier;
+    int32_t sh_degree;        /* active degree 0..3 */
+    int32_t sh_coeffs;        /* K = coefficients stored per Gaussian (stride of shs) */
+    int32_t prefiltered;
+    int32_t debug;            /* 1: synchronise + check after every kernel */
+    int32_t tile_row_begin;   /* tile-row band rendered by this rank (multi-GPU shard) */
+    int32_t tile_row_end;     /* exclusive; (0, ceil(H/16)) = whole image; (0,0) is also whole image */
+    int32_t depth_normalize;  /* 1: returned depth = D/alpha (expected depth), 0: raw sum */
+    const float* viewmatrix;  /* [16] device */
+    const float* projmatrix;  /* [16] device */
+    const float* campos;      /* [3]  device */
+    const float* bg;          /* [3]  device */
+} TgsSettings;
+
+/* Per-Gaussian inputs (replaces the tensor arguments of rasterize_gaussians). */
+typedef struct TgsGaussians {
+    int32_t N;
+    const float* means3D;        /* [N,3] */
+    const float* opacities;      /* [N]   */
+    const float* shs;            /* [N,K,3] or NULL */
+    const float* colors_precomp; /* [N,3]   or NULL  (exactly one of shs / colors_precomp) */
+    const float* scales;         /* [N,3]   or NULL */
+    const float* rotations;      /* [N,4]   or NULL  (w,x,y,z), used as given */
+    const float* cov3D_precomp;  /* [N,6]   or NULL  (exactly one of (scales,rotations) / cov3D_precomp) */
+} TgsGaussians;
+
+/* Fused touch-depth supervision. target==NULL or mode==NONE disables it. */
+typedef struct TgsTouch {
+    const float* target;   /* [H,W] metres (x scene scale); 0 = invalid  (reference utils/fuse_touch_vision.py:372-388) */
+    const float* weight;   /* [H,W] per-pixel weight (e.g. 1/sigma) or NULL = 1 */
+    const float* scale;    /* device scalar: depth_loss_mult / Z  (see tgs_touch_loss_scale) */
+    int32_t mode;          /* TGS_LOSS_* */
+} TgsTouch;
+
+/* Saved state handed from forward to backward. */
+typedef struct TgsSaved {
+    void*   geom;          /* TGS_BUF_GEOM    */
+    void*   binning;       /* TGS_BUF_BINNING */
+    void*   image;         /* TGS_BUF_IMAGE   */
+    int64_t num_rendered;  /* I */
+} TgsSaved;
+
+/* Gradient outputs of backward (all device, fully written by the kernels: no memset needed). */
+typedef struct TgsGrads {
+    float* dmeans2D;   /* [N,3] NDC-scaled mean gradient (x*0.5W, y*0.5H, 0): densifier statistic */
+    float* dmeans3D;   /* [N,3] */
+    float* dopacity;   /* [N]   */
+    float* dshs;       /* [N,K,3] or NULL */
+    float* dcolors;    /* [N,3]   or NULL */
+    float* dscales;    /* [N,3]   or NULL */
+    float* drotations; /* [N,4]   or NULL */
+    float* dcov3D;     /* [N,6]   or NULL */
+} TgsGrads;
+
+int         tgs_abi_version(void);
+const char* tgs_last_error(void);
+/* number of kernels this library has launched in this process (own kernels, CUB kernels) */
+void        tgs_launch_counts(uint64_t* own, uint64_t* cub);
+
+/* replaces markVisible: present[i] = view-space z > 0.2 */
+int tgs_mark_visible(int32_t N, const float* means3D, const float* viewmatrix,
+                     uint8_t* present, void* stream);
+
+/*
+ * replaces RasterizeGaussiansCUDA.
+ * Outputs: out_color [3,H,W], out_depth [H,W], out_alpha [H,W], radii [N] (int32),
+ * saved (buffers come from `alloc`).  One stream-synchronising D2H read of num_rendered.
+ * Pixels outside this rank's tile-row band are left untouched.
+ */
+int tgs_forward(const TgsSettings* s, const TgsGaussians* g,
+                tgs_alloc_fn alloc, void* alloc_user,
+                float* out_color, float* out_depth, float* out_alpha, int32_t* radii,
+                TgsSaved* saved, void* stream);
+
+/*
+ * replaces BACKWARD::render with the touch-depth gradient fused in.
+ * dL_dcolor [3,H,W]; dL_ddepth / dL_dalpha [H,W] or NULL (external autograd grads on the
+ * returned depth / alpha);  residual_out [H,W] or NULL.
+ * screen_grads [N,10] = (dx,dy (pixel units), dA,dB,dC, dopacity, dr,dg,db, ddepth) is
+ * ZEROED then accumulated: this is the buffer the multi-GPU path all-reduces.
+ */
+int tgs_backward_render(const TgsSettings* s, const TgsGaussians* g, const TgsSaved* saved,
+                        const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
+                        const TgsTouch* touch, float* residual_out,
+                        float* screen_grads, void* stream);
+
+/* replaces BACKWARD::preprocess: screen_grads -> parameter gradients. */
+int tgs_backward_preprocess(const TgsSettings* s, const TgsGaussians* g, const TgsSaved* saved,
+                            const int32_t* radii, const float* screen_grads,
+                            const TgsGrads* grads, void* stream);
+
+/* replaces RasterizeGaussiansBackwardCUDA: tgs_backward_render + tgs_backward_preprocess. */
+int tgs_backward(const TgsSettings* s, const TgsGaussians* g, const TgsSaved* saved,
+                 const int32_t* radii,
+                 const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
+                 const TgsTouch* touch, float* residual_out,
+                 float* screen_grads, const TgsGrads* grads, void* stream);
+
+/*
+ * scale_out[0] = mult / max(1, #(target > 0))   (or mult / norm when norm > 0);
+ * scale_out[1] is an integer workspace.  scale_out: 2 x 4 bytes, device.
+ * (loss multiplier semantics: reference legacy/model_tactile.py:162; validity = depth > 0:
+ *  reference utils/fuse_touch_vision.py:51,109)
+ */
+int tgs_touch_loss_scale(const float* target, int64_t num_pixels, float mult, float norm,
+                         float* scale_out, void* stream);
+
+/*
+ * Host-buffer convenience used by the end-to-end measurement: every pointer in g / settings /
+ * touch / outputs is a HOST pointer; the call uploads, runs forward + backward with
+ * dL_dcolor = sign(color - gt_rgb)/(3HW) (L1 photometric) and the fused touch loss, and downloads
+ * the parameter gradients.  Scratch is allocated with cudaMallocAsync.  Returns the photometric
+ * loss in *loss_host.
+ */
+int tgs_train_step_host(const TgsSettings* s_host, const TgsGaussians* g_host,
+                        const float* gt_rgb_host, const float* touch_target_host,
+                        const float* touch_weight_host, int32_t loss_mode, float depth_loss_mult,
+                        const TgsGrads* grads_host, float* out_color_host, float* out_depth_host,
+                        int32_t* radii_host, float* loss_host, int64_t* num_rendered_host,
+                        void* stream);
+
+/* introspection used by tests: layout of the saved buffers (byte offsets from the base) */
+typedef struct TgsGeomLayout {
+    size_t xy, depth, cov3D, conic_opacity, rgb, tiles_touched, offsets, clamped, rect, total;
+} TgsGeomLayout;
+typedef struct TgsBinningLayout {
+    size_t keys_unsorted, vals_unsorted, keys_sorted, vals_sorted, ranges, records, total;
+} TgsBinningLayout;
+typedef struct TgsImageLayout {
+    size_t final_T, n_contrib, depth_raw, total;
+} TgsImageLayout;
+int tgs_geom_layout(int32_t N, TgsGeomLayout* out);
+int tgs_binning_layout(int64_t num_rendered, int32_t num_tiles, TgsBinningLayout* out);
+int tgs_image_layout(int32_t W, int32_t H, TgsImageLayout* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TGS_H_ */
