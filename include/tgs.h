@@ -114,6 +114,25 @@ const char* tgs_last_error(void);
 /* number of kernels this library has launched in this process (own kernels, CUB kernels) */
 void        tgs_launch_counts(uint64_t* own, uint64_t* cub);
 
+/*
+ * Stage timers: when enabled, every kernel stage is bracketed by cudaEventRecord on the launching
+ * stream (what bench.py's roofline uses: per-launch durations measured live inside the timed region).
+ * tgs_profile_read synchronises nothing: call it after the stream is idle.  It returns, per stage,
+ * the accumulated milliseconds and launch count since the last read, then resets.
+ */
+#define TGS_STAGE_PREPROCESS      0
+#define TGS_STAGE_SCAN            1
+#define TGS_STAGE_DUPLICATE       2
+#define TGS_STAGE_SORT            3
+#define TGS_STAGE_PACK            4
+#define TGS_STAGE_RENDER_FWD      5
+#define TGS_STAGE_LOSS_SCALE      6
+#define TGS_STAGE_RENDER_BWD      7
+#define TGS_STAGE_PREPROCESS_BWD  8
+#define TGS_NUM_STAGES            9
+int tgs_profile_enable(int32_t on);
+int tgs_profile_read(float* ms_per_stage, int32_t* launches_per_stage);
+
 /* replaces markVisible: present[i] = view-space z > 0.2 */
 int tgs_mark_visible(int32_t N, const float* means3D, const float* viewmatrix,
                      uint8_t* present, void* stream);
@@ -122,11 +141,14 @@ int tgs_mark_visible(int32_t N, const float* means3D, const float* viewmatrix,
  * replaces RasterizeGaussiansCUDA.
  * Outputs: out_color [3,H,W], out_depth [H,W], out_alpha [H,W], radii [N] (int32),
  * saved (buffers come from `alloc`).  One stream-synchronising D2H read of num_rendered.
+ * touch_target / residual_out [H,W] (both or neither NULL): residual = depth - target where
+ * target > 0 and alpha > 0, else 0 (logging value of the touch-depth loss).
  * Pixels outside this rank's tile-row band are left untouched.
  */
 int tgs_forward(const TgsSettings* s, const TgsGaussians* g,
                 tgs_alloc_fn alloc, void* alloc_user,
                 float* out_color, float* out_depth, float* out_alpha, int32_t* radii,
+                const float* touch_target, float* residual_out,
                 TgsSaved* saved, void* stream);
 
 /*
@@ -163,11 +185,13 @@ int tgs_touch_loss_scale(const float* target, int64_t num_pixels, float mult, fl
                          float* scale_out, void* stream);
 
 /*
- * Host-buffer convenience used by the end-to-end measurement: every pointer in g / settings /
- * touch / outputs is a HOST pointer; the call uploads, runs forward + backward with
- * dL_dcolor = sign(color - gt_rgb)/(3HW) (L1 photometric) and the fused touch loss, and downloads
- * the parameter gradients.  Scratch is allocated with cudaMallocAsync.  Returns the photometric
- * loss in *loss_host.
+ * Host-buffer entry point (the call a non-PyTorch trainer makes; timed by the end-to-end bench with
+ * every host<->device copy inside the timed region).  EVERY pointer reachable from s_host / g_host /
+ * grads_host and every *_host argument is a HOST pointer (NULL = absent / not wanted).  The call
+ * uploads, runs forward, forms dL/dcolor = sign(color - gt_rgb)/(3HW) (L1 photometric; zero when
+ * gt_rgb_host is NULL) plus the fused touch loss (mode/mult as in TgsTouch, Z = #(target>0)), runs
+ * backward and downloads what was asked for.  Scratch comes from cudaMallocAsync on `stream`.
+ * *loss_host receives the photometric loss.  Synchronises the stream before returning.
  */
 int tgs_train_step_host(const TgsSettings* s_host, const TgsGaussians* g_host,
                         const float* gt_rgb_host, const float* touch_target_host,
@@ -178,13 +202,31 @@ int tgs_train_step_host(const TgsSettings* s_host, const TgsGaussians* g_host,
 
 /* introspection used by tests: layout of the saved buffers (byte offsets from the base) */
 typedef struct TgsGeomLayout {
-    size_t xy, depth, cov3D, conic_opacity, rgb, tiles_touched, offsets, clamped, rect, total;
+    size_t records;        /* TgsRecord[N]: 3 x float4 = (x,y,depth,id) (A,B,C,opacity) (r,g,b,-) */
+    size_t cov3D;          /* float[N,6] */
+    size_t tiles_touched;  /* uint32[N] */
+    size_t offsets;        /* uint32[N] inclusive scan */
+    size_t clamped;        /* uint8[N] bit c = colour channel c clamped */
+    size_t rect;           /* uint32[N,2]: (rminx | rmaxx<<16, rminy | rmaxy<<16) */
+    size_t scan_temp;
+    size_t total;
 } TgsGeomLayout;
 typedef struct TgsBinningLayout {
-    size_t keys_unsorted, vals_unsorted, keys_sorted, vals_sorted, ranges, records, total;
+    size_t ranges;         /* uint32[T,2] */
+    size_t records;        /* TgsRecord[I], depth-sorted per tile, contiguous */
+    size_t keys_sorted;    /* uint64[I] (tile << 32 | depth bits) */
+    size_t vals_sorted;    /* uint32[I] Gaussian ids */
+    size_t keys_unsorted;  /* uint64[I] */
+    size_t vals_unsorted;  /* uint32[I] */
+    size_t sort_temp;
+    size_t sort_temp_bytes;
+    size_t total;
 } TgsBinningLayout;
 typedef struct TgsImageLayout {
-    size_t final_T, n_contrib, depth_raw, total;
+    size_t final_T;        /* float[H,W] */
+    size_t n_contrib;      /* uint32[H,W] */
+    size_t depth_raw;      /* float[H,W] un-normalised sum depth*alpha*T */
+    size_t total;
 } TgsImageLayout;
 int tgs_geom_layout(int32_t N, TgsGeomLayout* out);
 int tgs_binning_layout(int64_t num_rendered, int32_t num_tiles, TgsBinningLayout* out);

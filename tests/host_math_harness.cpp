@@ -26,7 +26,10 @@ void hm_preprocess(int N, const float* means, const float* scales, const float* 
         out_rgb[3 * i] = out_rgb[3 * i + 1] = out_rgb[3 * i + 2] = 0.0f;
         out_clamped[i] = 0;
         if (vis && shs) {
-            tgs_sh_forward(cam->deg, shs + 3 * cam->K * i, means[3 * i] - campos[0],
+            float sh48[48];
+            int nb = (cam->deg + 1) * (cam->deg + 1);
+            for (int k = 0; k < 48; ++k) sh48[k] = (k < 3 * nb) ? shs[3 * cam->K * i + k] : 0.0f;
+            tgs_sh_forward(cam->deg, sh48, means[3 * i] - campos[0],
                            means[3 * i + 1] - campos[1], means[3 * i + 2] - campos[2],
                            out_rgb + 3 * i, out_clamped[i]);
         }
@@ -47,10 +50,15 @@ void hm_backward(int N, const float* means, const float* scales, const float* ro
             else tgs_cov3d(scales + 3 * i, cam->mod, rots + 4 * i, cov);
             tgs_project_backward(vm, pm, *cam, means[3 * i], means[3 * i + 1], means[3 * i + 2], cov,
                                  sg + 10 * i, dm, dc);
-            if (shs)
-                tgs_sh_backward(cam->deg, cam->K, shs + 3 * cam->K * i, means[3 * i] - campos[0],
+            if (shs) {
+                float sh48[48], dsh48[48];
+                int nb = (cam->deg + 1) * (cam->deg + 1);
+                for (int k = 0; k < 48; ++k) sh48[k] = (k < 3 * nb) ? shs[3 * cam->K * i + k] : 0.0f;
+                tgs_sh_backward(cam->deg, cam->K, sh48, means[3 * i] - campos[0],
                                 means[3 * i + 1] - campos[1], means[3 * i + 2] - campos[2],
-                                sg + 10 * i + 6, clamped[i], dsh + 3 * cam->K * i, dm);
+                                sg + 10 * i + 6, clamped[i], dsh48, dm);
+                for (int k = 0; k < 3 * cam->K; ++k) dsh[3 * cam->K * i + k] = dsh48[k];
+            }
             if (!cov_pre) tgs_cov3d_backward(scales + 3 * i, cam->mod, rots + 4 * i, dc, ds, dq);
         } else if (shs) {
             for (int k = 0; k < 3 * cam->K; ++k) dsh[3 * cam->K * i + k] = 0.0f;

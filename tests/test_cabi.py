@@ -1,0 +1,82 @@
+"""CPU checks of the drop-in boundary: libtgs.so loads, exports every symbol include/tgs.h declares,
+its struct layouts match the ctypes mirror, and argument errors are reported without touching a GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from helpers import ROOT, T
+
+
+def _declared_functions():
+    txt = open(os.path.join(ROOT, "include", "tgs.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = re.findall(r"\b(tgs_[a-z0-9_]+)\s*\(", txt)
+    return sorted(set(n for n in names if n != "tgs_alloc_fn"))
+
+
+def test_header_symbols_exported(tgs_lib):
+    decl = _declared_functions()
+    assert len(decl) >= 12
+    for name in decl:
+        assert hasattr(tgs_lib, name), f"{name} declared in include/tgs.h but not exported by libtgs.so"
+    assert set(decl) == set(T._lib.SIGNATURES), "ctypes SIGNATURES out of sync with include/tgs.h"
+    assert tgs_lib.tgs_abi_version() == T._lib.TGS_ABI_VERSION
+
+
+def test_layouts_are_aligned_and_monotone(tgs_lib):
+    L = T._lib
+    g = L.TgsGeomLayout(); tgs_lib.tgs_geom_layout(1000, C.byref(g))
+    assert g.records == 0 and g.cov3D >= 48 * 1000 and g.total >= g.rect + 8 * 1000
+    for n, _ in g._fields_:
+        assert getattr(g, n) % 256 == 0
+    b = L.TgsBinningLayout(); tgs_lib.tgs_binning_layout(5000, 64, C.byref(b))
+    assert b.records >= 64 * 8 and b.keys_sorted >= b.records + 48 * 5000
+    i = L.TgsImageLayout(); tgs_lib.tgs_image_layout(100, 50, C.byref(i))
+    assert i.total >= 3 * 4 * 5000
+
+
+def test_argument_errors_without_gpu(tgs_lib):
+    L = T._lib
+    s = L.TgsSettings(image_width=64, image_height=64, tanfovx=0.5, tanfovy=0.5, scale_modifier=1.0)
+    g = L.TgsGaussians(N=4)
+    saved = L.TgsSaved()
+    cb = L.ALLOC_FN(lambda u, w, n: None)
+    rc = tgs_lib.tgs_forward(C.byref(s), C.byref(g), cb, None, None, None, None, None, None, None, C.byref(saved), None)
+    assert rc == -1 and b"viewmatrix" in tgs_lib.tgs_last_error()
+    s.viewmatrix = s.projmatrix = s.bg = s.campos = 0x1000      # never dereferenced: validation fails first
+    g.means3D = g.opacities = 0x1000
+    rc = tgs_lib.tgs_forward(C.byref(s), C.byref(g), cb, None, None, None, None, None, None, None, C.byref(saved), None)
+    assert rc == -1 and b"exactly one of either SHs or precomputed colors" in tgs_lib.tgs_last_error()
+    g.colors_precomp = 0x1000
+    g.scales = 0x1000
+    rc = tgs_lib.tgs_forward(C.byref(s), C.byref(g), cb, None, None, None, None, None, None, None, C.byref(saved), None)
+    assert rc == -1 and b"scale/rotation pair" in tgs_lib.tgs_last_error()
+    rc = tgs_lib.tgs_mark_visible(3, None, None, None, None)
+    assert rc == -1
+
+
+def test_operator_rejects_cpu_tensors_and_bad_combos(tgs_lib):
+    import torch
+    cam = T.synth.look_at_camera(32, 32, (0.0, 0.0, -3.0))
+    rs = T.GaussianRasterizationSettings(32, 32, cam.tanfovx, cam.tanfovy, torch.zeros(3), 1.0, cam.viewmatrix,
+                                         cam.projmatrix, 0, cam.campos)
+    r = T.GaussianRasterizer(rs)
+    m = torch.zeros(4, 3); o = torch.ones(4, 1); sh = torch.zeros(4, 1, 3); sc = torch.ones(4, 3); q = torch.zeros(4, 4)
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(m, None, o, shs=None, colors_precomp=None, scales=sc, rotations=q)
+    with pytest.raises(Exception, match="scale/rotation pair"):
+        r(m, None, o, shs=sh, scales=sc, rotations=q, cov3D_precomp=torch.zeros(4, 6))
+    with pytest.raises(RuntimeError, match="CUDA-only"):      # loud failure, never a CPU fallback
+        r(m, None, o, shs=sh, scales=sc, rotations=q)
+
+
+def test_product_path_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under touch-gs_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "touch-gs_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(import oracle|from oracle)", txt, flags=re.M), os.path.join(dp, f)

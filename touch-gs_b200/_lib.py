@@ -1,0 +1,154 @@
+"""ctypes binding of libtgs.so (the C ABI declared in ``include/tgs.h``).
+
+The library is the product: if it is missing or fails to load, importing the operator raises --
+there is NO CPU fallback and nothing here ever imports ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtgs.so")
+
+TGS_ABI_VERSION = 1
+BUF_GEOM, BUF_BINNING, BUF_IMAGE, BUF_TEMP = 0, 1, 2, 3
+LOSS_NONE, LOSS_L1, LOSS_L2 = 0, 1, 2
+LOSS_MODES = {"none": LOSS_NONE, "l1": LOSS_L1, "l2": LOSS_L2}
+NGRAD = 10
+
+c_fp = C.c_void_p  # all device pointers travel as void*
+
+
+class TgsSettings(C.Structure):
+    _fields_ = [
+        ("image_width", C.c_int32), ("image_height", C.c_int32),
+        ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
+        ("sh_degree", C.c_int32), ("sh_coeffs", C.c_int32),
+        ("prefiltered", C.c_int32), ("debug", C.c_int32),
+        ("tile_row_begin", C.c_int32), ("tile_row_end", C.c_int32),
+        ("depth_normalize", C.c_int32),
+        ("viewmatrix", c_fp), ("projmatrix", c_fp), ("campos", c_fp), ("bg", c_fp),
+    ]
+
+
+class TgsGaussians(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32),
+        ("means3D", c_fp), ("opacities", c_fp), ("shs", c_fp), ("colors_precomp", c_fp),
+        ("scales", c_fp), ("rotations", c_fp), ("cov3D_precomp", c_fp),
+    ]
+
+
+class TgsTouch(C.Structure):
+    _fields_ = [("target", c_fp), ("weight", c_fp), ("scale", c_fp), ("mode", C.c_int32)]
+
+
+class TgsSaved(C.Structure):
+    _fields_ = [("geom", c_fp), ("binning", c_fp), ("image", c_fp), ("num_rendered", C.c_int64)]
+
+
+class TgsGrads(C.Structure):
+    _fields_ = [
+        ("dmeans2D", c_fp), ("dmeans3D", c_fp), ("dopacity", c_fp), ("dshs", c_fp),
+        ("dcolors", c_fp), ("dscales", c_fp), ("drotations", c_fp), ("dcov3D", c_fp),
+    ]
+
+
+class TgsGeomLayout(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in
+                ("records", "cov3D", "tiles_touched", "offsets", "clamped", "rect", "scan_temp", "total")]
+
+
+class TgsBinningLayout(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in
+                ("ranges", "records", "keys_sorted", "vals_sorted", "keys_unsorted", "vals_unsorted",
+                 "sort_temp", "sort_temp_bytes", "total")]
+
+
+class TgsImageLayout(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in ("final_T", "n_contrib", "depth_raw", "total")]
+
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int, C.c_size_t)
+
+# every symbol include/tgs.h declares: (restype, argtypes)
+SIGNATURES = {
+    "tgs_abi_version": (C.c_int, []),
+    "tgs_last_error": (C.c_char_p, []),
+    "tgs_launch_counts": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "tgs_profile_enable": (C.c_int, [C.c_int32]),
+    "tgs_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "tgs_mark_visible": (C.c_int, [C.c_int32, c_fp, c_fp, c_fp, c_fp]),
+    "tgs_forward": (C.c_int, [C.POINTER(TgsSettings), C.POINTER(TgsGaussians), ALLOC_FN, C.c_void_p,
+                              c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, C.POINTER(TgsSaved), c_fp]),
+    "tgs_backward_render": (C.c_int, [C.POINTER(TgsSettings), C.POINTER(TgsGaussians), C.POINTER(TgsSaved),
+                                      c_fp, c_fp, c_fp, C.POINTER(TgsTouch), c_fp, c_fp, c_fp]),
+    "tgs_backward_preprocess": (C.c_int, [C.POINTER(TgsSettings), C.POINTER(TgsGaussians), C.POINTER(TgsSaved),
+                                          c_fp, c_fp, C.POINTER(TgsGrads), c_fp]),
+    "tgs_backward": (C.c_int, [C.POINTER(TgsSettings), C.POINTER(TgsGaussians), C.POINTER(TgsSaved), c_fp,
+                               c_fp, c_fp, c_fp, C.POINTER(TgsTouch), c_fp, c_fp, C.POINTER(TgsGrads), c_fp]),
+    "tgs_touch_loss_scale": (C.c_int, [c_fp, C.c_int64, C.c_float, C.c_float, c_fp, c_fp]),
+    "tgs_train_step_host": (C.c_int, [C.POINTER(TgsSettings), C.POINTER(TgsGaussians), c_fp, c_fp, c_fp,
+                                      C.c_int32, C.c_float, C.POINTER(TgsGrads), c_fp, c_fp, c_fp, c_fp,
+                                      C.POINTER(C.c_int64), c_fp]),
+    "tgs_geom_layout": (C.c_int, [C.c_int32, C.POINTER(TgsGeomLayout)]),
+    "tgs_binning_layout": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(TgsBinningLayout)]),
+    "tgs_image_layout": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(TgsImageLayout)]),
+}
+
+_lib = None
+
+
+class TgsError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load libtgs.so; raise loudly if the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension is not built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (or `python touch-gs_b200/build.py`). "
+            "There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so is stale / a symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    ver = lib.tgs_abi_version()
+    if ver != TGS_ABI_VERSION:
+        raise ImportError(f"libtgs.so ABI version {ver} != expected {TGS_ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().tgs_last_error()
+        raise TgsError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+STAGES = ("preprocess", "scan", "duplicate", "sort", "pack", "render_fwd", "loss_scale", "render_bwd",
+          "preprocess_bwd")
+
+
+def profile_enable(on: bool) -> None:
+    load().tgs_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """{stage: (ms_total, launches)} since the last read; call after synchronising the stream."""
+    ms = (C.c_float * len(STAGES))()
+    cnt = (C.c_int32 * len(STAGES))()
+    load().tgs_profile_read(ms, cnt)
+    return {n: (float(ms[i]), int(cnt[i])) for i, n in enumerate(STAGES)}
+
+
+def launch_counts():
+    own, cub = C.c_uint64(0), C.c_uint64(0)
+    load().tgs_launch_counts(C.byref(own), C.byref(cub))
+    return int(own.value), int(cub.value)

@@ -1,0 +1,279 @@
+// api.cu -- the C ABI of libtgs.so (include/tgs.h): argument checking, saved-buffer layouts and
+// the host-side orchestration of the kernels.  No torch types; the Python host layer
+// (touch-gs_b200/rasterizer.py) binds these with ctypes.
+#include "tgs_common.cuh"
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+// ------------------------------------------------------------------------------- errors
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_own{0}, g_cub{0};
+
+void tgs_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int tgs_check_cuda(cudaError_t e, const char* what, const char* file, int line) {
+    if (e == cudaSuccess) return 0;
+    tgs_set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return (int)e;
+}
+void tgs_count_own(int n) { g_own += (uint64_t)n; }
+void tgs_count_cub(int n) { g_cub += (uint64_t)n; }
+
+// -------------------------------------------------------------------------- stage timers
+#include <mutex>
+namespace {
+struct ProfPair { cudaEvent_t a, b; int stage; };
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfPair> g_prof_pairs;      // recorded since the last read
+std::vector<ProfPair> g_prof_free;       // recycled events
+cudaEvent_t g_prof_open[TGS_NUM_STAGES];
+}  // namespace
+void tgs_prof_begin(int stage, cudaStream_t st) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfPair p;
+    if (!g_prof_free.empty()) { p = g_prof_free.back(); g_prof_free.pop_back(); }
+    else { if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return; }
+    p.stage = stage;
+    cudaEventRecord(p.a, st);
+    g_prof_open[stage] = p.a;
+    g_prof_pairs.push_back(p);
+}
+void tgs_prof_end(int stage, cudaStream_t st) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto it = g_prof_pairs.rbegin(); it != g_prof_pairs.rend(); ++it)
+        if (it->stage == stage && it->a == g_prof_open[stage]) { cudaEventRecord(it->b, st); break; }
+}
+extern "C" int tgs_profile_enable(int32_t on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = on != 0;
+    return 0;
+}
+extern "C" int tgs_profile_read(float* ms, int32_t* cnt) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int i = 0; i < TGS_NUM_STAGES; ++i) { if (ms) ms[i] = 0.f; if (cnt) cnt[i] = 0; }
+    for (auto& p : g_prof_pairs) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) { if (ms) ms[p.stage] += t; if (cnt) cnt[p.stage] += 1; }
+        g_prof_free.push_back(p);
+    }
+    g_prof_pairs.clear();
+    cudaGetLastError();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------- layouts
+namespace {
+struct Carver {
+    size_t off = 0;
+    size_t take(size_t bytes) { size_t o = off; off = tgs_align_up(off + bytes); return o; }
+};
+int ceil_log2(uint32_t v) { int b = 0; while ((1u << b) < v) ++b; return b; }
+}  // namespace
+
+extern "C" int tgs_geom_layout(int32_t N, TgsGeomLayout* o) {
+    Carver c; size_t n = (size_t)(N > 0 ? N : 0);
+    o->records = c.take(n * sizeof(TgsRecord));
+    o->cov3D = c.take(n * 6 * sizeof(float));
+    o->tiles_touched = c.take(n * sizeof(uint32_t));
+    o->offsets = c.take(n * sizeof(uint32_t));
+    o->clamped = c.take(n);
+    o->rect = c.take(n * sizeof(uint2));
+    o->scan_temp = c.take(tgs_scan_temp_bytes(N > 0 ? N : 1));
+    o->total = c.off > 0 ? c.off : TGS_ALIGN;
+    return 0;
+}
+extern "C" int tgs_binning_layout(int64_t I, int32_t T, TgsBinningLayout* o) {
+    Carver c; size_t n = (size_t)(I > 0 ? I : 0);
+    int end_bit = 32 + ceil_log2((uint32_t)(T > 1 ? T : 2));
+    o->ranges = c.take((size_t)T * sizeof(uint2));
+    o->records = c.take(n * sizeof(TgsRecord));
+    o->keys_sorted = c.take(n * sizeof(uint64_t));
+    o->vals_sorted = c.take(n * sizeof(uint32_t));
+    o->keys_unsorted = c.take(n * sizeof(uint64_t));
+    o->vals_unsorted = c.take(n * sizeof(uint32_t));
+    o->sort_temp_bytes = tgs_sort_temp_bytes(I > 0 ? I : 1, end_bit);
+    o->sort_temp = c.take(o->sort_temp_bytes);
+    o->total = c.off;
+    return 0;
+}
+extern "C" int tgs_image_layout(int32_t W, int32_t H, TgsImageLayout* o) {
+    Carver c; size_t p = (size_t)W * H;
+    o->final_T = c.take(p * 4);
+    o->n_contrib = c.take(p * 4);
+    o->depth_raw = c.take(p * 4);
+    o->total = c.off;
+    return 0;
+}
+
+GeomView tgs_geom_view(void* base, int N) {
+    TgsGeomLayout l; tgs_geom_layout(N, &l);
+    char* b = (char*)base; GeomView v;
+    v.records = (TgsRecord*)(b + l.records); v.cov3D = (float*)(b + l.cov3D);
+    v.tiles_touched = (uint32_t*)(b + l.tiles_touched); v.offsets = (uint32_t*)(b + l.offsets);
+    v.clamped = (uint8_t*)(b + l.clamped); v.rect = (uint2*)(b + l.rect);
+    return v;
+}
+BinView tgs_bin_view(void* base, int64_t I, int T) {
+    TgsBinningLayout l; tgs_binning_layout(I, T, &l);
+    char* b = (char*)base; BinView v;
+    v.ranges = (uint2*)(b + l.ranges); v.records = (TgsRecord*)(b + l.records);
+    v.keys_sorted = (uint64_t*)(b + l.keys_sorted); v.vals_sorted = (uint32_t*)(b + l.vals_sorted);
+    v.keys_unsorted = (uint64_t*)(b + l.keys_unsorted); v.vals_unsorted = (uint32_t*)(b + l.vals_unsorted);
+    v.cub_temp = b + l.sort_temp; v.cub_temp_bytes = l.sort_temp_bytes;
+    return v;
+}
+ImageView tgs_image_view(void* base, int W, int H) {
+    TgsImageLayout l; tgs_image_layout(W, H, &l);
+    char* b = (char*)base; ImageView v;
+    v.final_T = (float*)(b + l.final_T); v.n_contrib = (uint32_t*)(b + l.n_contrib);
+    v.depth_raw = (float*)(b + l.depth_raw);
+    return v;
+}
+
+// ---------------------------------------------------------------------------- validation
+static int check_inputs(const TgsSettings* s, const TgsGaussians* g) {
+    if (!s || !g) { tgs_set_error("NULL settings / gaussians"); return TGS_EINVAL; }
+    if (s->image_width <= 0 || s->image_height <= 0) { tgs_set_error("bad image size %dx%d", s->image_width, s->image_height); return TGS_EINVAL; }
+    if (s->image_width > 65535 * TGS_TILE || s->image_height > 65535 * TGS_TILE) { tgs_set_error("image too large"); return TGS_EINVAL; }
+    if (g->N < 0) { tgs_set_error("negative N"); return TGS_EINVAL; }
+    if (!s->viewmatrix || !s->projmatrix || !s->bg) { tgs_set_error("viewmatrix / projmatrix / bg must be non-NULL"); return TGS_EINVAL; }
+    if (g->N > 0) {
+        if (!g->means3D || !g->opacities) { tgs_set_error("means3D / opacities must be non-NULL"); return TGS_EINVAL; }
+        if ((g->shs == nullptr) == (g->colors_precomp == nullptr)) {
+            tgs_set_error("Please provide exactly one of either SHs or precomputed colors!"); return TGS_EINVAL; }
+        bool sr = g->scales != nullptr && g->rotations != nullptr;
+        bool any_sr = g->scales != nullptr || g->rotations != nullptr;
+        if ((sr == (g->cov3D_precomp != nullptr)) || (any_sr && !sr)) {
+            tgs_set_error("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!"); return TGS_EINVAL; }
+        if (g->shs) {
+            if (s->sh_degree < 0 || s->sh_degree > 3) { tgs_set_error("sh_degree %d out of range 0..3", s->sh_degree); return TGS_EINVAL; }
+            int need = (s->sh_degree + 1) * (s->sh_degree + 1);
+            if (s->sh_coeffs < need || s->sh_coeffs > 16) { tgs_set_error("sh_coeffs %d incompatible with degree %d", s->sh_coeffs, s->sh_degree); return TGS_EINVAL; }
+            if (!s->campos) { tgs_set_error("campos must be non-NULL with SHs"); return TGS_EINVAL; }
+        }
+    }
+    return 0;
+}
+
+static uint32_t* pinned_word() {
+    static thread_local uint32_t* p = nullptr;
+    if (!p) { if (cudaHostAlloc((void**)&p, 64, cudaHostAllocDefault) != cudaSuccess) p = nullptr; }
+    return p;
+}
+
+// ------------------------------------------------------------------------------ C ABI
+extern "C" int tgs_abi_version(void) { return TGS_ABI_VERSION; }
+extern "C" const char* tgs_last_error(void) { return g_err; }
+extern "C" void tgs_launch_counts(uint64_t* own, uint64_t* cub) {
+    if (own) *own = g_own.load();
+    if (cub) *cub = g_cub.load();
+}
+
+extern "C" int tgs_mark_visible(int32_t N, const float* means3D, const float* viewmatrix, uint8_t* present, void* stream) {
+    if (N < 0 || (N > 0 && (!means3D || !viewmatrix || !present))) { tgs_set_error("tgs_mark_visible: bad arguments"); return TGS_EINVAL; }
+    return tgs_launch_mark_visible(N, means3D, viewmatrix, present, (cudaStream_t)stream);
+}
+
+extern "C" int tgs_forward(const TgsSettings* s, const TgsGaussians* g, tgs_alloc_fn alloc, void* user,
+                           float* out_color, float* out_depth, float* out_alpha, int32_t* radii,
+                           const float* touch_target, float* residual_out,
+                           TgsSaved* saved, void* stream) {
+    int rc = check_inputs(s, g);
+    if (rc) return rc;
+    if (!alloc || !saved || !out_color || !out_depth || !out_alpha || (g->N > 0 && !radii)) {
+        tgs_set_error("tgs_forward: NULL output / allocator"); return TGS_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const TgsCam cam = tgs_make_cam(s);
+    const int N = g->N, T = cam.Tx * cam.Ty;
+
+    TgsGeomLayout gl; tgs_geom_layout(N, &gl);
+    TgsImageLayout il; tgs_image_layout(cam.W, cam.H, &il);
+    void* geom = alloc(user, TGS_BUF_GEOM, gl.total);
+    void* image = alloc(user, TGS_BUF_IMAGE, il.total);
+    if (!geom || !image) { tgs_set_error("allocator returned NULL"); return TGS_ENOMEM; }
+    GeomView gv = tgs_geom_view(geom, N);
+    ImageView iv = tgs_image_view(image, cam.W, cam.H);
+
+    int64_t I = 0;
+    if (N > 0) {
+        rc = tgs_launch_preprocess(cam, s, g, gv, radii, st); if (rc) return rc;
+        rc = tgs_scan_tiles(gv, N, (char*)geom + gl.scan_temp, tgs_scan_temp_bytes(N), st); if (rc) return rc;
+        uint32_t* hp = pinned_word();
+        if (!hp) { tgs_set_error("cudaHostAlloc failed"); return TGS_ENOMEM; }
+        TGS_CUDA(cudaMemcpyAsync(hp, gv.offsets + (N - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        TGS_CUDA(cudaStreamSynchronize(st));   // the one host sync of the forward
+        I = (int64_t)*hp;
+    }
+    TgsBinningLayout bl; tgs_binning_layout(I, T, &bl);
+    void* binning = alloc(user, TGS_BUF_BINNING, bl.total);
+    if (!binning) { tgs_set_error("allocator returned NULL"); return TGS_ENOMEM; }
+    BinView bv = tgs_bin_view(binning, I, T);
+    if (I > 0) {
+        rc = tgs_launch_duplicate(gv, N, cam.Tx, bv, st); if (rc) return rc;
+        int end_bit = 32 + ceil_log2((uint32_t)(T > 1 ? T : 2));
+        rc = tgs_sort_instances(bv, I, end_bit, st); if (rc) return rc;
+        if (s->debug) TGS_CUDA(cudaStreamSynchronize(st));
+    }
+    rc = tgs_launch_pack_ranges(gv, bv, I, T, st); if (rc) return rc;
+    if (s->debug) TGS_CUDA(cudaStreamSynchronize(st));
+    if ((touch_target == nullptr) != (residual_out == nullptr)) { tgs_set_error("touch_target and residual_out go together"); return TGS_EINVAL; }
+    rc = tgs_launch_render_fwd(cam, s, bv, iv, out_color, out_depth, out_alpha, touch_target, residual_out, st); if (rc) return rc;
+    saved->geom = geom; saved->binning = binning; saved->image = image; saved->num_rendered = I;
+    return 0;
+}
+
+extern "C" int tgs_backward_render(const TgsSettings* s, const TgsGaussians* g, const TgsSaved* saved,
+                                   const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
+                                   const TgsTouch* touch, float* residual_out, float* screen_grads, void* stream) {
+    int rc = check_inputs(s, g);
+    if (rc) return rc;
+    if (!saved || !saved->geom || !saved->binning || !saved->image) { tgs_set_error("tgs_backward_render: saved buffers missing"); return TGS_ESTATE; }
+    if (!dL_dcolor || (g->N > 0 && !screen_grads)) { tgs_set_error("tgs_backward_render: NULL gradient buffers"); return TGS_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const TgsCam cam = tgs_make_cam(s);
+    BinView bv = tgs_bin_view(saved->binning, saved->num_rendered, cam.Tx * cam.Ty);
+    ImageView iv = tgs_image_view(saved->image, cam.W, cam.H);
+    if (g->N > 0) TGS_CUDA(cudaMemsetAsync(screen_grads, 0, sizeof(float) * TGS_NGRAD * (size_t)g->N, st));
+    return tgs_launch_render_bwd(cam, s, bv, iv, dL_dcolor, dL_ddepth, dL_dalpha, touch, residual_out, screen_grads, st);
+}
+
+extern "C" int tgs_backward_preprocess(const TgsSettings* s, const TgsGaussians* g, const TgsSaved* saved,
+                                       const int32_t* radii, const float* screen_grads, const TgsGrads* grads, void* stream) {
+    int rc = check_inputs(s, g);
+    if (rc) return rc;
+    if (g->N == 0) return 0;
+    if (!saved || !saved->geom) { tgs_set_error("tgs_backward_preprocess: saved buffers missing"); return TGS_ESTATE; }
+    if (!radii || !screen_grads || !grads || !grads->dmeans2D || !grads->dmeans3D || !grads->dopacity) {
+        tgs_set_error("tgs_backward_preprocess: NULL gradient buffers"); return TGS_EINVAL; }
+    if (g->shs && !grads->dshs) { tgs_set_error("dshs required when shs given"); return TGS_EINVAL; }
+    if (g->colors_precomp && !grads->dcolors) { tgs_set_error("dcolors required when colors_precomp given"); return TGS_EINVAL; }
+    if (g->scales && (!grads->dscales || !grads->drotations)) { tgs_set_error("dscales/drotations required"); return TGS_EINVAL; }
+    if (g->cov3D_precomp && !grads->dcov3D) { tgs_set_error("dcov3D required when cov3D_precomp given"); return TGS_EINVAL; }
+    const TgsCam cam = tgs_make_cam(s);
+    GeomView gv = tgs_geom_view(saved->geom, g->N);
+    return tgs_launch_preprocess_bwd(cam, s, g, gv, radii, screen_grads, grads, (cudaStream_t)stream);
+}
+
+extern "C" int tgs_backward(const TgsSettings* s, const TgsGaussians* g, const TgsSaved* saved, const int32_t* radii,
+                            const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
+                            const TgsTouch* touch, float* residual_out, float* screen_grads,
+                            const TgsGrads* grads, void* stream) {
+    int rc = tgs_backward_render(s, g, saved, dL_dcolor, dL_ddepth, dL_dalpha, touch, residual_out, screen_grads, stream);
+    if (rc) return rc;
+    return tgs_backward_preprocess(s, g, saved, radii, screen_grads, grads, stream);
+}
+
+extern "C" int tgs_touch_loss_scale(const float* target, int64_t num_pixels, float mult, float norm, float* scale_out, void* stream) {
+    if (!scale_out || (norm <= 0.0f && num_pixels > 0 && !target)) { tgs_set_error("tgs_touch_loss_scale: bad arguments"); return TGS_EINVAL; }
+    return tgs_launch_loss_scale(target, num_pixels, mult, norm, scale_out, (cudaStream_t)stream);
+}

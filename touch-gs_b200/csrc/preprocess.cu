@@ -1,0 +1,222 @@
+// preprocess.cu -- per-Gaussian kernels: forward projection, its backward (A9)
+// and markVisible.  THIS TRANSLATION UNIT IS COMPILED WITH --fmad=false so that the integer
+// results derived from float math (radius, tile rectangle, depth sort key) are bit-identical to
+// the oracle (oracle/gs_oracle.py::preprocess), which rounds every operation separately.
+//
+// Roofline: HBM.  Algorithmic bytes per Gaussian: forward reads 4*(11+3K) and writes
+// a 48 B record + 24 B cov3D + 4 B tiles + 4 B radii + 8 B rect + 1 B clamp mask; backward reads the
+// parameters again plus 40 B screen gradients and writes 4*(11+3K)+12 B of gradients.
+#include "tgs_common.cuh"
+
+namespace {
+
+constexpr int kBlock = 256;
+
+struct CamMats { float vm[16]; float pm[16]; float cp[3]; };
+
+__device__ __forceinline__ void load_cam(const float* vm, const float* pm, const float* cp, CamMats* sm) {
+    int t = threadIdx.x;
+    if (t < 16) sm->vm[t] = vm[t];
+    else if (t < 32) sm->pm[t - 16] = pm[t - 16];
+    else if (t < 35) sm->cp[t - 32] = cp ? cp[t - 32] : 0.0f;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_preprocess(int N, const float* __restrict__ means, const float* __restrict__ scales,
+             const float* __restrict__ rots, const float* __restrict__ opac,
+             const float* __restrict__ shs, const float* __restrict__ colors,
+             const float* __restrict__ covpre, const float* __restrict__ vm,
+             const float* __restrict__ pm, const float* __restrict__ campos, TgsCam cam,
+             TgsRecord* __restrict__ rec, float* __restrict__ cov3D,
+             uint32_t* __restrict__ tiles, uint8_t* __restrict__ clamped,
+             uint2* __restrict__ rect, int32_t* __restrict__ radii) {
+    __shared__ CamMats cm;
+    load_cam(vm, pm, campos, &cm);
+    int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= N) return;
+    float x = means[3 * i], y = means[3 * i + 1], z = means[3 * i + 2];
+    float cov[6];
+    if (covpre) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) cov[k] = covpre[6 * i + k];
+    } else {
+        float4 q = reinterpret_cast<const float4*>(rots)[i];
+        float sc[3] = {scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]};
+        float qq[4] = {q.x, q.y, q.z, q.w};
+        tgs_cov3d(sc, cam.mod, qq, cov);
+    }
+    TgsProj p;
+    bool vis = tgs_project(cm.vm, cm.pm, cam, x, y, z, cov, p);
+    float rgb[3] = {0.f, 0.f, 0.f};
+    unsigned cl = 0;
+    if (vis) {
+        if (shs) {
+            // K*3 contiguous floats per Gaussian; 16-byte loads (K*12 B is a multiple of 16 for K in {1,4,9,16}
+            // only when K*3 % 4 == 0, so fall back to scalar loads otherwise)
+            float sh[48];
+#pragma unroll
+            for (int k = 0; k < 48; ++k) sh[k] = 0.0f;
+            const float* src = shs + (size_t)3 * cam.K * i;
+            int nb = (cam.deg + 1) * (cam.deg + 1);
+            if (((3 * cam.K) & 3) == 0) {
+                const float4* s4 = reinterpret_cast<const float4*>(src);
+                int n4 = (3 * nb + 3) >> 2;
+#pragma unroll
+                for (int k = 0; k < 12; ++k)
+                    if (k < n4) {
+                        float4 v = __ldg(s4 + k);
+                        // entries above 3*nb may belong to inactive bands: mask them to zero
+                        sh[4 * k] = (4 * k < 3 * nb) ? v.x : 0.0f;
+                        sh[4 * k + 1] = (4 * k + 1 < 3 * nb) ? v.y : 0.0f;
+                        sh[4 * k + 2] = (4 * k + 2 < 3 * nb) ? v.z : 0.0f;
+                        sh[4 * k + 3] = (4 * k + 3 < 3 * nb) ? v.w : 0.0f;
+                    }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 48; ++k)
+                    if (k < 3 * nb) sh[k] = __ldg(src + k);
+            }
+            tgs_sh_forward(cam.deg, sh, x - cm.cp[0], y - cm.cp[1], z - cm.cp[2], rgb, cl);
+        } else {
+            rgb[0] = colors[3 * i]; rgb[1] = colors[3 * i + 1]; rgb[2] = colors[3 * i + 2];
+        }
+    }
+    TgsRecord r;
+    r.a = make_float4(p.px, p.py, p.depth, __int_as_float(i));
+    r.b = make_float4(p.conA, p.conB, p.conC, vis ? opac[i] : 0.0f);
+    r.c = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
+    rec[i] = r;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cov3D[6 * i + k] = cov[k];
+    tiles[i] = (uint32_t)p.tiles;
+    clamped[i] = (uint8_t)cl;
+    rect[i] = make_uint2((uint32_t)p.rminx | ((uint32_t)p.rmaxx << 16),
+                         (uint32_t)p.rminy | ((uint32_t)p.rmaxy << 16));
+    radii[i] = p.radius;
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_preprocess_bwd(int N, const float* __restrict__ means, const float* __restrict__ scales,
+                 const float* __restrict__ rots, const float* __restrict__ shs,
+                 const float* __restrict__ covpre, const float* __restrict__ vm,
+                 const float* __restrict__ pm, const float* __restrict__ campos, TgsCam cam,
+                 const float* __restrict__ cov3D, const uint8_t* __restrict__ clamped,
+                 const int32_t* __restrict__ radii, const float* __restrict__ sgrad,
+                 float* __restrict__ dmeans2D, float* __restrict__ dmeans3D,
+                 float* __restrict__ dopacity, float* __restrict__ dshs, float* __restrict__ dcolors,
+                 float* __restrict__ dscales, float* __restrict__ drots, float* __restrict__ dcov3D) {
+    __shared__ CamMats cm;
+    load_cam(vm, pm, campos, &cm);
+    int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= N) return;
+    float dm[3] = {0.f, 0.f, 0.f}, dc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float ds[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
+    float sg[TGS_NGRAD];
+#pragma unroll
+    for (int k = 0; k < TGS_NGRAD; ++k) sg[k] = 0.0f;
+    bool vis = radii[i] > 0;
+    if (vis) {
+        const float2* s2 = reinterpret_cast<const float2*>(sgrad + (size_t)TGS_NGRAD * i);
+#pragma unroll
+        for (int k = 0; k < TGS_NGRAD / 2; ++k) { float2 v = s2[k]; sg[2 * k] = v.x; sg[2 * k + 1] = v.y; }
+        float x = means[3 * i], y = means[3 * i + 1], z = means[3 * i + 2];
+        float cov[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) cov[k] = cov3D[6 * i + k];
+        tgs_project_backward(cm.vm, cm.pm, cam, x, y, z, cov, sg, dm, dc);
+        if (shs) {
+            float sh[48], dsh[48];
+            const float* src = shs + (size_t)3 * cam.K * i;
+            int nb = (cam.deg + 1) * (cam.deg + 1);
+#pragma unroll
+            for (int k = 0; k < 48; ++k) sh[k] = (k < 3 * nb) ? __ldg(src + k) : 0.0f;
+            tgs_sh_backward(cam.deg, cam.K, sh, x - cm.cp[0], y - cm.cp[1], z - cm.cp[2],
+                            sg + 6, clamped[i], dsh, dm);
+            float* dst = dshs + (size_t)3 * cam.K * i;
+            if (((3 * cam.K) & 3) == 0) {
+                float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+                for (int k = 0; k < 12; ++k)
+                    if (4 * k < 3 * cam.K) d4[k] = make_float4(dsh[4 * k], dsh[4 * k + 1], dsh[4 * k + 2], dsh[4 * k + 3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 48; ++k)
+                    if (k < 3 * cam.K) dst[k] = dsh[k];
+            }
+        }
+        if (!covpre) {
+            float4 q = reinterpret_cast<const float4*>(rots)[i];
+            float sc[3] = {scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]};
+            float qq[4] = {q.x, q.y, q.z, q.w};
+            tgs_cov3d_backward(sc, cam.mod, qq, dc, ds, dq);
+        }
+    } else if (dshs) {
+        float* dst = dshs + (size_t)3 * cam.K * i;
+        for (int k = 0; k < 3 * cam.K; ++k) dst[k] = 0.0f;
+    }
+    dmeans2D[3 * i] = sg[0] * 0.5f * (float)cam.W;
+    dmeans2D[3 * i + 1] = sg[1] * 0.5f * (float)cam.H;
+    dmeans2D[3 * i + 2] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dmeans3D[3 * i + k] = dm[k];
+    dopacity[i] = sg[5];
+    if (dcolors) { dcolors[3 * i] = sg[6]; dcolors[3 * i + 1] = sg[7]; dcolors[3 * i + 2] = sg[8]; }
+    if (dscales) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dscales[3 * i + k] = ds[k];
+    }
+    if (drots) reinterpret_cast<float4*>(drots)[i] = make_float4(dq[0], dq[1], dq[2], dq[3]);
+    if (dcov3D) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) dcov3D[6 * i + k] = dc[k];
+    }
+}
+
+__global__ void k_mark_visible(int N, const float* __restrict__ means, const float* __restrict__ vm,
+                               uint8_t* __restrict__ present) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float tz = tgs_xform(vm, means[3 * i], means[3 * i + 1], means[3 * i + 2], 2);
+    present[i] = tz > TGS_NEAR_Z ? 1 : 0;
+}
+
+}  // namespace
+
+int tgs_launch_preprocess(const TgsCam& cam, const TgsSettings* s, const TgsGaussians* g,
+                          GeomView gv, int32_t* radii, cudaStream_t st) {
+    int N = g->N;
+    if (N == 0) return 0;
+    TgsProfScope prof(TGS_STAGE_PREPROCESS, st);
+    k_preprocess<<<(N + kBlock - 1) / kBlock, kBlock, 0, st>>>(
+        N, g->means3D, g->scales, g->rotations, g->opacities, g->shs, g->colors_precomp,
+        g->cov3D_precomp, s->viewmatrix, s->projmatrix, s->campos, cam, gv.records, gv.cov3D,
+        gv.tiles_touched, gv.clamped, gv.rect, radii);
+    tgs_count_own(1);
+    TGS_KERNEL_CHECK(st, s->debug);
+    return 0;
+}
+
+int tgs_launch_preprocess_bwd(const TgsCam& cam, const TgsSettings* s, const TgsGaussians* g,
+                              GeomView gv, const int32_t* radii, const float* screen_grads,
+                              const TgsGrads* gr, cudaStream_t st) {
+    int N = g->N;
+    if (N == 0) return 0;
+    TgsProfScope prof(TGS_STAGE_PREPROCESS_BWD, st);
+    k_preprocess_bwd<<<(N + kBlock - 1) / kBlock, kBlock, 0, st>>>(
+        N, g->means3D, g->scales, g->rotations, g->shs, g->cov3D_precomp, s->viewmatrix,
+        s->projmatrix, s->campos, cam, gv.cov3D, gv.clamped, radii, screen_grads, gr->dmeans2D,
+        gr->dmeans3D, gr->dopacity, g->shs ? gr->dshs : nullptr, gr->dcolors, gr->dscales,
+        gr->drotations, gr->dcov3D);
+    tgs_count_own(1);
+    TGS_KERNEL_CHECK(st, s->debug);
+    return 0;
+}
+
+int tgs_launch_mark_visible(int N, const float* means, const float* vm, uint8_t* present, cudaStream_t st) {
+    if (N == 0) return 0;
+    k_mark_visible<<<(N + 255) / 256, 256, 0, st>>>(N, means, vm, present);
+    tgs_count_own(1);
+    TGS_CUDA(cudaGetLastError());
+    return 0;
+}

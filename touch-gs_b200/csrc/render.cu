@@ -1,0 +1,394 @@
+// render.cu -- per-tile alpha compositing and its backward with the touch-depth
+// gradient fused into the same traversal (A6), plus the tiny loss-scale reduction.
+//
+// B200 design
+//   * one CTA per 16x16 tile, one thread per pixel, a warp covers an 8x4 pixel patch;
+//   * the tile's depth-sorted list is a CONTIGUOUS run of 48-byte records (binning.cu packs it), so
+//     each batch of 256 records (12 KB) is brought into shared memory by ONE TMA bulk copy
+//     (cp.async.bulk ... mbarrier::complete_tx::bytes), double-buffered: the copy of batch b+2 is
+//     issued as soon as batch b has been consumed, so HBM/L2 latency is hidden behind the blend;
+//   * forward: RGB, expected depth and alpha are composited in ONE traversal;
+//   * backward: back-to-front replay; the per-pixel depth / alpha gradients are computed IN-KERNEL
+//     from the touch target, its weight and the loss scale (no autograd round trip through HBM);
+//     the 10 per-Gaussian gradient values are reduced across the warp with a 12-shuffle
+//     reduce-scatter butterfly (instead of 10 x 5 shuffles) and land in HBM as 10 REDs per
+//     (warp, Gaussian) instead of 320 per-thread atomics.
+//   No tensor cores: the path is gather/blend, not a dense contraction.
+//
+// Roofline: HBM.  Algorithmic bytes: forward 48 B/instance + 24 B/pixel written;
+// backward 48 B/instance read + 40 B/instance accumulated + 32 B/pixel.
+#include "tgs_common.cuh"
+
+namespace {
+
+constexpr int kBatch = 256;                 // records per TMA stage
+constexpr uint32_t kRecBytes = 48;
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// power = -0.5*(A dx^2 + C dy^2) - B dx dy with a PINNED rounding sequence: forward and backward must
+// take bit-identical skip decisions (power > 0, alpha < 1/255) for every (pixel, splat) pair, so the
+// contraction into FMAs is spelled out instead of being left to the compiler per kernel.
+__device__ __forceinline__ float splat_power(const float4 q, float dx, float dy) {
+    const float ax = __fmul_rn(q.x, dx);
+    const float cy = __fmul_rn(q.z, dy);
+    const float s = __fmaf_rn(cy, dy, __fmul_rn(ax, dx));
+    const float bxy = __fmul_rn(__fmul_rn(q.y, dx), dy);
+    return __fmaf_rn(-0.5f, s, -bxy);
+}
+__device__ __forceinline__ float splat_alpha(float opacity, float G) {
+    return fminf(TGS_ALPHA_MAX, __fmul_rn(opacity, G));
+}
+
+struct PixelMap {
+    int px, py, pix; bool inside; float fx, fy;
+};
+__device__ __forceinline__ PixelMap map_pixel(int tile, int Tx, int W, int H) {
+    PixelMap m;
+    int tx = tile % Tx, ty = tile / Tx;
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    m.px = tx * TGS_TILE + (warp & 1) * 8 + (lane & 7);
+    m.py = ty * TGS_TILE + (warp >> 1) * 4 + (lane >> 3);
+    m.inside = (m.px < W) && (m.py < H);
+    m.pix = m.py * W + m.px;
+    m.fx = (float)m.px; m.fy = (float)m.py;
+    return m;
+}
+
+// ------------------------------------------------------------------------------- forward
+__global__ void __launch_bounds__(256)
+k_render_fwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ recs, int W, int H, int Tx,
+             int row0, const float* __restrict__ bg, int normalize, float* __restrict__ out_color,
+             float* __restrict__ out_depth, float* __restrict__ out_alpha, float* __restrict__ final_T,
+             uint32_t* __restrict__ n_contrib, float* __restrict__ depth_raw,
+             const float* __restrict__ t_target, float* __restrict__ residual) {
+    __shared__ __align__(128) float4 sbuf[2][kBatch * 3];
+    __shared__ __align__(8) uint64_t full[2];
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x + row0 * Tx;
+    const PixelMap pm = map_pixel(tile, Tx, W, H);
+    const uint2 rng = ranges[tile];
+    const int len = (int)(rng.y - rng.x);
+    const int nb = (len + kBatch - 1) / kBatch;
+    if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    const TgsRecord* src = recs + rng.x;
+    auto issue = [&](int b) {
+        int cnt = min(kBatch, len - b * kBatch);
+        uint32_t bytes = (uint32_t)cnt * kRecBytes;
+        mbar_expect_tx(&full[b & 1], bytes);
+        tma_bulk_g2s(sbuf[b & 1], src + (size_t)b * kBatch, bytes, &full[b & 1]);
+    };
+    if (tid == 0) { if (nb > 0) issue(0); if (nb > 1) issue(1); }
+
+    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
+    uint32_t last = 0;
+    bool done = !pm.inside;
+    int b = 0;
+    for (; b < nb; ++b) {
+        mbar_wait(&full[b & 1], (uint32_t)((b >> 1) & 1));
+        if (!done) {
+            const float4* s = sbuf[b & 1];
+            const int cnt = min(kBatch, len - b * kBatch);
+            for (int j = 0; j < cnt; ++j) {
+                const float4 a = s[3 * j], q = s[3 * j + 1];
+                const float dx = a.x - pm.fx, dy = a.y - pm.fy;
+                const float power = splat_power(q, dx, dy);
+                if (power > 0.0f) continue;
+                const float alpha = splat_alpha(q.w, __expf(power));
+                if (alpha < TGS_ALPHA_MIN) continue;
+                const float test_T = T * (1.0f - alpha);
+                if (test_T < TGS_T_EPS) { done = true; break; }
+                const float4 c = s[3 * j + 2];
+                const float w = alpha * T;
+                C0 += c.x * w; C1 += c.y * w; C2 += c.z * w; D += a.z * w;
+                T = test_T;
+                last = (uint32_t)(b * kBatch + j + 1);
+            }
+        }
+        const int nd = __syncthreads_count(done);
+        if (nd == 256) break;
+        if (tid == 0 && b + 2 < nb) issue(b + 2);
+    }
+    // a copy issued for batch b+1 may still be in flight if we broke out early: the CTA must not
+    // retire (and free its shared memory) before it lands.
+    if (tid == 0 && b < nb && b + 1 < nb) mbar_wait(&full[(b + 1) & 1], (uint32_t)(((b + 1) >> 1) & 1));
+
+    if (pm.inside) {
+        const size_t HW = (size_t)W * H;
+        out_color[pm.pix] = C0 + T * bg[0];
+        out_color[HW + pm.pix] = C1 + T * bg[1];
+        out_color[2 * HW + pm.pix] = C2 + T * bg[2];
+        const float A = 1.0f - T;
+        out_alpha[pm.pix] = A;
+        const float dhat = normalize ? (A > 0.0f ? D / A : 0.0f) : D;
+        out_depth[pm.pix] = dhat;
+        if (residual) {
+            const float tgt = t_target[pm.pix];
+            residual[pm.pix] = (tgt > 0.0f && A > 0.0f) ? dhat - tgt : 0.0f;
+        }
+        final_T[pm.pix] = T;
+        n_contrib[pm.pix] = last;
+        depth_raw[pm.pix] = D;
+    }
+}
+
+// ------------------------------------------------------------------------------ backward
+// Reduce-scatter of 10 per-lane values across the warp in 12 shuffles.  On return lane L holds in
+// `out` the warp-wide sum of value `slot` if `valid`.
+__device__ __forceinline__ void warp_reduce_scatter10(const float (&v)[TGS_NGRAD], int lane, float& out,
+                                                      int& slot, bool& valid) {
+    bool h = lane & 16;
+    float r[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        float send = h ? v[k] : v[k + 5];
+        float keep = h ? v[k + 5] : v[k];
+        r[k] = keep + __shfl_xor_sync(kFull, send, 16);
+    }
+    h = lane & 8;
+    float s0 = (h ? r[3] : r[0]) + __shfl_xor_sync(kFull, h ? r[0] : r[3], 8);
+    float s1 = (h ? r[4] : r[1]) + __shfl_xor_sync(kFull, h ? r[1] : r[4], 8);
+    float s2 = (h ? 0.0f : r[2]) + __shfl_xor_sync(kFull, h ? r[2] : 0.0f, 8);
+    h = lane & 4;
+    float t0 = (h ? s2 : s0) + __shfl_xor_sync(kFull, h ? s0 : s2, 4);
+    float t1 = (h ? 0.0f : s1) + __shfl_xor_sync(kFull, h ? s1 : 0.0f, 4);
+    h = lane & 2;
+    float u = (h ? t1 : t0) + __shfl_xor_sync(kFull, h ? t0 : t1, 2);
+    u += __shfl_xor_sync(kFull, u, 1);
+    out = u;
+    slot = ((lane & 16) ? 5 : 0) + ((lane & 8) ? 3 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+    valid = !(lane & 1) && ((lane & 8) ? !(lane & 4) : !((lane & 4) && (lane & 2)));
+}
+
+__global__ void __launch_bounds__(256)
+k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ recs, int W, int H, int Tx,
+             int row0, const float* __restrict__ bg, int normalize, const float* __restrict__ final_T,
+             const uint32_t* __restrict__ n_contrib, const float* __restrict__ depth_raw,
+             const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
+             const float* __restrict__ dL_dalpha, const float* __restrict__ t_target,
+             const float* __restrict__ t_weight, const float* __restrict__ t_scale, int t_mode,
+             float* __restrict__ residual, float* __restrict__ sgrad) {
+    __shared__ __align__(128) float4 sbuf[2][kBatch * 3];
+    __shared__ __align__(8) uint64_t full[2];
+    __shared__ uint32_t s_max[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x + row0 * Tx;
+    const PixelMap pm = map_pixel(tile, Tx, W, H);
+    const uint2 rng = ranges[tile];
+    const int len = (int)(rng.y - rng.x);
+
+    // ---- per-pixel state and the FUSED touch-depth gradient (SURVEY A6 "Fusion")
+    float Tf = 1.0f, g0 = 0.f, g1 = 0.f, g2 = 0.f, gD = 0.f, gA = 0.f;
+    uint32_t nc = 0;
+    if (pm.inside) {
+        const size_t HW = (size_t)W * H;
+        Tf = final_T[pm.pix];
+        nc = n_contrib[pm.pix];
+        g0 = dL_dcolor[pm.pix]; g1 = dL_dcolor[HW + pm.pix]; g2 = dL_dcolor[2 * HW + pm.pix];
+        const float A = 1.0f - Tf;
+        const float D = depth_raw[pm.pix];
+        float gDhat = dL_ddepth ? dL_ddepth[pm.pix] : 0.0f;
+        gA = dL_dalpha ? dL_dalpha[pm.pix] : 0.0f;
+        float res = 0.0f;
+        if (t_target != nullptr && A > 0.0f) {
+            const float tgt = t_target[pm.pix];
+            if (tgt > 0.0f) {
+                const float dhat = normalize ? D / A : D;
+                res = dhat - tgt;
+                if (t_mode != TGS_LOSS_NONE) {
+                    const float wgt = (t_weight ? t_weight[pm.pix] : 1.0f) * t_scale[0];
+                    gDhat += (t_mode == TGS_LOSS_L1)
+                                 ? wgt * (float)((res > 0.0f) - (res < 0.0f))
+                                 : 2.0f * wgt * res;
+                }
+            }
+        }
+        if (residual) residual[pm.pix] = res;
+        if (normalize) {
+            if (A > 0.0f) { gD = gDhat / A; gA -= gDhat * D / (A * A); }
+        } else {
+            gD = gDhat;
+        }
+    }
+    const float bgdot = bg[0] * g0 + bg[1] * g1 + bg[2] * g2;
+    // colour: d(T_final*bg)/dalpha_i = -T_final/(1-alpha_i) * bg ; alpha: dA/dalpha_i = +T_final/(1-alpha_i)
+    const float tail = Tf * (gA - bgdot);
+
+    // ---- nothing beyond the deepest contributor of any pixel of the tile needs replaying
+    uint32_t m = nc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(kFull, m, o));
+    if (lane == 0) s_max[warp] = m;
+    if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    uint32_t mx = s_max[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) mx = max(mx, s_max[k]);
+    const int leff = min(len, (int)mx);
+    const int nb = (leff + kBatch - 1) / kBatch;
+    if (nb == 0) return;
+
+    const TgsRecord* src = recs + rng.x;
+    // sequence step q processes batch nb-1-q (back to front)
+    auto issue = [&](int q) {
+        int b = nb - 1 - q;
+        int cnt = min(kBatch, leff - b * kBatch);
+        uint32_t bytes = (uint32_t)cnt * kRecBytes;
+        mbar_expect_tx(&full[q & 1], bytes);
+        tma_bulk_g2s(sbuf[q & 1], src + (size_t)b * kBatch, bytes, &full[q & 1]);
+    };
+    if (tid == 0) { issue(0); if (nb > 1) issue(1); }
+
+    float T = Tf, last_alpha = 0.f;
+    float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, lcD = 0.f;      // colour / depth of the splat behind
+    float ac0 = 0.f, ac1 = 0.f, ac2 = 0.f, acD = 0.f;      // colour / depth accumulated behind
+    for (int q = 0; q < nb; ++q) {
+        mbar_wait(&full[q & 1], (uint32_t)((q >> 1) & 1));
+        const int b = nb - 1 - q;
+        const int cnt = min(kBatch, leff - b * kBatch);
+        const float4* s = sbuf[q & 1];
+        for (int j = cnt - 1; j >= 0; --j) {
+            const uint32_t idx = (uint32_t)(b * kBatch + j);
+            const float4 a = s[3 * j], cq = s[3 * j + 1];
+            const float dx = a.x - pm.fx, dy = a.y - pm.fy;
+            const float power = splat_power(cq, dx, dy);
+            const float G = __expf(power);
+            const float alpha = splat_alpha(cq.w, G);
+            const bool valid = (idx < nc) && (power <= 0.0f) && (alpha >= TGS_ALPHA_MIN);
+            if (!__any_sync(kFull, valid)) continue;
+            float v[TGS_NGRAD];
+#pragma unroll
+            for (int k = 0; k < TGS_NGRAD; ++k) v[k] = 0.0f;
+            if (valid) {
+                const float4 c = s[3 * j + 2];
+                const float inv = 1.0f / (1.0f - alpha);
+                T = T * inv;                               // transmittance in front of this splat
+                const float w = alpha * T;
+                const float om = 1.0f - last_alpha;
+                ac0 = last_alpha * lc0 + om * ac0; lc0 = c.x;
+                ac1 = last_alpha * lc1 + om * ac1; lc1 = c.y;
+                ac2 = last_alpha * lc2 + om * ac2; lc2 = c.z;
+                acD = last_alpha * lcD + om * acD; lcD = a.z;
+                float dLda = (c.x - ac0) * g0 + (c.y - ac1) * g1 + (c.z - ac2) * g2 + (a.z - acD) * gD;
+                dLda = dLda * T + tail * inv;
+                last_alpha = alpha;
+                const float dLdG = cq.w * dLda;
+                const float gdx = G * dx, gdy = G * dy;
+                v[0] = dLdG * (-gdx * cq.x - gdy * cq.y);
+                v[1] = dLdG * (-gdy * cq.z - gdx * cq.y);
+                v[2] = -0.5f * gdx * dx * dLdG;
+                v[3] = -gdx * dy * dLdG;
+                v[4] = -0.5f * gdy * dy * dLdG;
+                v[5] = G * dLda;
+                v[6] = w * g0; v[7] = w * g1; v[8] = w * g2;
+                v[9] = w * gD;
+            }
+            float sum; int slot; bool ok;
+            warp_reduce_scatter10(v, lane, sum, slot, ok);
+            if (ok) atomicAdd(sgrad + (size_t)__float_as_int(a.w) * TGS_NGRAD + slot, sum);
+        }
+        __syncthreads();
+        if (tid == 0 && q + 2 < nb) issue(q + 2);
+    }
+}
+
+// -------------------------------------------------------------------- touch loss scale
+__global__ void k_count_valid(const float* __restrict__ target, int64_t P, unsigned int* __restrict__ counter) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned int c = 0;
+    for (; i < P; i += stride) c += target[i] > 0.0f ? 1u : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(counter, c);
+}
+__global__ void k_finish_scale(float mult, float norm, float* out) {
+    unsigned int cnt = reinterpret_cast<unsigned int*>(out)[1];
+    float Z = norm > 0.0f ? norm : fmaxf(1.0f, (float)cnt);
+    out[0] = mult / Z;
+}
+
+}  // namespace
+
+int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, BinView bv, ImageView iv,
+                          float* out_color, float* out_depth, float* out_alpha,
+                          const float* touch_target, float* residual_out, cudaStream_t st) {
+    int nt = cam.Tx * (cam.row1 - cam.row0);
+    if (nt <= 0) return 0;
+    TgsProfScope prof(TGS_STAGE_RENDER_FWD, st);
+    k_render_fwd<<<nt, 256, 0, st>>>(bv.ranges, bv.records, cam.W, cam.H, cam.Tx, cam.row0, s->bg,
+                                     s->depth_normalize, out_color, out_depth, out_alpha, iv.final_T,
+                                     iv.n_contrib, iv.depth_raw, touch_target, residual_out);
+    tgs_count_own(1);
+    TGS_KERNEL_CHECK(st, s->debug);
+    return 0;
+}
+
+int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, BinView bv, ImageView iv,
+                          const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
+                          const TgsTouch* touch, float* residual, float* screen_grads, cudaStream_t st) {
+    int nt = cam.Tx * (cam.row1 - cam.row0);
+    if (nt <= 0) return 0;
+    const float* tt = nullptr; const float* tw = nullptr; const float* ts = nullptr; int mode = TGS_LOSS_NONE;
+    if (touch && touch->target) {
+        tt = touch->target; tw = touch->weight; ts = touch->scale; mode = touch->mode;
+        if (mode != TGS_LOSS_NONE && ts == nullptr) { tgs_set_error("touch loss enabled but scale pointer is NULL"); return TGS_EINVAL; }
+    }
+    TgsProfScope prof(TGS_STAGE_RENDER_BWD, st);
+    k_render_bwd<<<nt, 256, 0, st>>>(bv.ranges, bv.records, cam.W, cam.H, cam.Tx, cam.row0, s->bg,
+                                     s->depth_normalize, iv.final_T, iv.n_contrib, iv.depth_raw, dL_dcolor,
+                                     dL_ddepth, dL_dalpha, tt, tw, ts, mode, residual, screen_grads);
+    tgs_count_own(1);
+    TGS_KERNEL_CHECK(st, s->debug);
+    return 0;
+}
+
+int tgs_launch_loss_scale(const float* target, int64_t P, float mult, float norm, float* out, cudaStream_t st) {
+    TgsProfScope prof(TGS_STAGE_LOSS_SCALE, st);
+    TGS_CUDA(cudaMemsetAsync(out, 0, 8, st));
+    if (norm <= 0.0f && P > 0) {
+        int blocks = (int)((P + 256 * 8 - 1) / (256 * 8));
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        k_count_valid<<<blocks, 256, 0, st>>>(target, P, reinterpret_cast<unsigned int*>(out) + 1);
+        tgs_count_own(1);
+    }
+    k_finish_scale<<<1, 1, 0, st>>>(mult, norm, out);
+    tgs_count_own(1);
+    TGS_CUDA(cudaGetLastError());
+    return 0;
+}

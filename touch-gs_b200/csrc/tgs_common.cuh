@@ -1,0 +1,110 @@
+// tgs_common.cuh -- shared declarations of libtgs.so (layouts of the saved buffers, the packed
+// per-instance record, error plumbing, kernel-launcher prototypes between translation units).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/tgs.h"
+#include "tgs_math.cuh"
+
+// ---------------------------------------------------------------------------------- records
+// One 48-byte record per Gaussian (geometry buffer) and, after the sort, one per tile instance
+// (binning buffer) so that every tile's depth-sorted list is CONTIGUOUS in HBM and can be moved
+// into shared memory by a single TMA bulk copy (cp.async.bulk) per batch.
+//   a = (x_pix, y_pix, depth, bits(gaussian id))
+//   b = (conic A, conic B, conic C, opacity)
+//   c = (r, g, b, unused)
+struct __align__(16) TgsRecord { float4 a, b, c; };
+static_assert(sizeof(TgsRecord) == 48, "record must be 48 bytes");
+
+#define TGS_ALIGN 256
+static inline size_t tgs_align_up(size_t v) { return (v + TGS_ALIGN - 1) / TGS_ALIGN * TGS_ALIGN; }
+
+// ------------------------------------------------------------------------------------ errors
+void tgs_set_error(const char* fmt, ...);
+int tgs_check_cuda(cudaError_t e, const char* what, const char* file, int line);
+#define TGS_CUDA(expr)                                                           \
+    do {                                                                         \
+        int _rc = tgs_check_cuda((expr), #expr, __FILE__, __LINE__);             \
+        if (_rc) return _rc;                                                     \
+    } while (0)
+// after a kernel launch: always peek the launch error; in debug mode also synchronise
+#define TGS_KERNEL_CHECK(stream, debug)                                          \
+    do {                                                                         \
+        TGS_CUDA(cudaGetLastError());                                            \
+        if (debug) TGS_CUDA(cudaStreamSynchronize(stream));                      \
+    } while (0)
+
+void tgs_count_own(int n);
+// stage timers (api.cu): no-ops unless tgs_profile_enable(1)
+void tgs_prof_begin(int stage, cudaStream_t st);
+void tgs_prof_end(int stage, cudaStream_t st);
+struct TgsProfScope {
+    int stage; cudaStream_t st;
+    TgsProfScope(int s, cudaStream_t t) : stage(s), st(t) { tgs_prof_begin(stage, st); }
+    ~TgsProfScope() { tgs_prof_end(stage, st); }
+};
+void tgs_count_cub(int n);
+
+// ---------------------------------------------------------------------- typed buffer views
+struct GeomView {
+    TgsRecord* records;      // [N]
+    float* cov3D;            // [N,6]
+    uint32_t* tiles_touched; // [N]
+    uint32_t* offsets;       // [N] inclusive scan
+    uint8_t* clamped;        // [N] bit c = colour channel c clamped at 0
+    uint2* rect;             // [N] (rminx | rmaxx<<16, rminy | rmaxy<<16)
+};
+struct BinView {
+    uint64_t* keys_unsorted; uint32_t* vals_unsorted;
+    uint64_t* keys_sorted;   uint32_t* vals_sorted;
+    uint2* ranges;           // [T]
+    TgsRecord* records;      // [I] packed, sorted
+    void* cub_temp; size_t cub_temp_bytes;
+};
+struct ImageView {
+    float* final_T; uint32_t* n_contrib; float* depth_raw;
+};
+GeomView tgs_geom_view(void* base, int N);
+BinView tgs_bin_view(void* base, int64_t I, int T);
+ImageView tgs_image_view(void* base, int W, int H);
+size_t tgs_sort_temp_bytes(int64_t I, int end_bit);
+size_t tgs_scan_temp_bytes(int N);
+
+// ------------------------------------------------------------------------ kernel launchers
+// preprocess.cu
+int tgs_launch_preprocess(const TgsCam& cam, const TgsSettings* s, const TgsGaussians* g,
+                          GeomView gv, int32_t* radii, cudaStream_t st);
+int tgs_launch_preprocess_bwd(const TgsCam& cam, const TgsSettings* s, const TgsGaussians* g,
+                              GeomView gv, const int32_t* radii, const float* screen_grads,
+                              const TgsGrads* grads, cudaStream_t st);
+int tgs_launch_mark_visible(int N, const float* means, const float* vm, uint8_t* present, cudaStream_t st);
+// binning.cu
+int tgs_scan_tiles(GeomView gv, int N, void* temp, size_t temp_bytes, cudaStream_t st);
+int tgs_launch_duplicate(GeomView gv, int N, int Tx, BinView bv, cudaStream_t st);
+int tgs_sort_instances(BinView bv, int64_t I, int end_bit, cudaStream_t st);
+int tgs_launch_pack_ranges(GeomView gv, BinView bv, int64_t I, int T, cudaStream_t st);
+// render.cu
+int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, BinView bv, ImageView iv,
+                          float* out_color, float* out_depth, float* out_alpha,
+                          const float* touch_target, float* residual_out, cudaStream_t st);
+int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, BinView bv, ImageView iv,
+                          const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
+                          const TgsTouch* touch, float* residual, float* screen_grads, cudaStream_t st);
+int tgs_launch_loss_scale(const float* target, int64_t P, float mult, float norm, float* out, cudaStream_t st);
+
+static inline TgsCam tgs_make_cam(const TgsSettings* s) {
+    TgsCam c;
+    c.W = s->image_width; c.H = s->image_height;
+    c.Tx = (c.W + TGS_TILE - 1) / TGS_TILE; c.Ty = (c.H + TGS_TILE - 1) / TGS_TILE;
+    c.fx = (float)c.W / (2.0f * s->tanfovx);
+    c.fy = (float)c.H / (2.0f * s->tanfovy);
+    c.limx = 1.3f * s->tanfovx; c.limy = 1.3f * s->tanfovy;
+    c.mod = s->scale_modifier;
+    c.row0 = s->tile_row_begin; c.row1 = s->tile_row_end;
+    if (c.row1 <= c.row0) { c.row0 = 0; c.row1 = c.Ty; }
+    if (c.row0 < 0) c.row0 = 0;
+    if (c.row1 > c.Ty) c.row1 = c.Ty;
+    c.deg = s->sh_degree; c.K = s->sh_coeffs;
+    return c;
+}

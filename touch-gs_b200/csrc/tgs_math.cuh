@@ -166,17 +166,22 @@ TGS_HD bool tgs_project(const float* vm, const float* pm, const TgsCam& cam,
 // sh: [K][3] for this Gaussian.  Returns rgb (+0.5, clamped >= 0) and the clamp mask (bit c).
 TGS_HD void tgs_sh_forward(int deg, const float* sh, float dx, float dy, float dz,
                            float* rgb, unsigned& clamped) {
+    // NOTE: `sh` must hold 48 floats with zeros above the active degree: all loops below run over
+    // the full 16 bases with compile-time indices so that device code keeps everything in registers.
     float ln = sqrtf((dx * dx + dy * dy) + dz * dz);
     float x = dx / ln, y = dy / ln, z = dz / ln;
     float b[16];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 16; ++k) b[k] = 0.0f;
     b[0] = TGS_SH_C0;
-    int nb = 1;
     if (deg > 0) {
-        b[1] = -TGS_SH_C1 * y; b[2] = TGS_SH_C1 * z; b[3] = -TGS_SH_C1 * x; nb = 4;
+        b[1] = -TGS_SH_C1 * y; b[2] = TGS_SH_C1 * z; b[3] = -TGS_SH_C1 * x;
         if (deg > 1) {
             float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
             b[4] = TGS_SH_C2_0 * xy; b[5] = TGS_SH_C2_1 * yz; b[6] = TGS_SH_C2_2 * (2.0f * zz - xx - yy);
-            b[7] = TGS_SH_C2_3 * xz; b[8] = TGS_SH_C2_4 * (xx - yy); nb = 9;
+            b[7] = TGS_SH_C2_3 * xz; b[8] = TGS_SH_C2_4 * (xx - yy);
             if (deg > 2) {
                 b[9] = TGS_SH_C3_0 * y * (3.0f * xx - yy);
                 b[10] = TGS_SH_C3_1 * xy * z;
@@ -185,14 +190,19 @@ TGS_HD void tgs_sh_forward(int deg, const float* sh, float dx, float dy, float d
                 b[13] = TGS_SH_C3_4 * x * (4.0f * zz - xx - yy);
                 b[14] = TGS_SH_C3_5 * z * (xx - yy);
                 b[15] = TGS_SH_C3_6 * x * (xx - 3.0f * yy);
-                nb = 16;
             }
         }
     }
     clamped = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
     for (int c = 0; c < 3; ++c) {
         float acc = 0.0f;
-        for (int k = 0; k < nb; ++k) acc += b[k] * sh[3 * k + c];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 16; ++k) acc += b[k] * sh[3 * k + c];
         acc += 0.5f;
         if (acc < 0.0f) { clamped |= (1u << c); acc = 0.0f; }
         rgb[c] = acc;
@@ -209,6 +219,9 @@ TGS_HD void tgs_sh_backward(int deg, int K, const float* sh, float dx, float dy,
     float inv = 1.0f / ln;
     float x = dx * inv, y = dy * inv, z = dz * inv;
     float b[16], bx[16], by[16], bz[16];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
     for (int k = 0; k < 16; ++k) { b[k] = bx[k] = by[k] = bz[k] = 0.0f; }
     b[0] = TGS_SH_C0;
     int nb = 1;
@@ -248,15 +261,17 @@ TGS_HD void tgs_sh_backward(int deg, int K, const float* sh, float dx, float dy,
             }
         }
     }
+    // `sh` holds 48 floats (zeros above the active degree); `dsh` receives 48 floats (zeros above it);
+    // the caller stores the first 3*K of them.  Full-length loops keep device code in registers.
+    (void)K; (void)nb;
     float ddx = 0.0f, ddy = 0.0f, ddz = 0.0f;
-    for (int k = 0; k < K; ++k) {
-        if (k < nb) {
-            float s = sh[3 * k] * g[0] + sh[3 * k + 1] * g[1] + sh[3 * k + 2] * g[2];
-            ddx += bx[k] * s; ddy += by[k] * s; ddz += bz[k] * s;
-            dsh[3 * k] = b[k] * g[0]; dsh[3 * k + 1] = b[k] * g[1]; dsh[3 * k + 2] = b[k] * g[2];
-        } else {
-            dsh[3 * k] = dsh[3 * k + 1] = dsh[3 * k + 2] = 0.0f;
-        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 16; ++k) {
+        float s = sh[3 * k] * g[0] + sh[3 * k + 1] * g[1] + sh[3 * k + 2] * g[2];
+        ddx += bx[k] * s; ddy += by[k] * s; ddz += bz[k] * s;
+        dsh[3 * k] = b[k] * g[0]; dsh[3 * k + 1] = b[k] * g[1]; dsh[3 * k + 2] = b[k] * g[2];
     }
     // d = raw/|raw| :  dL/draw = (dd - d (d.dd)) / |raw|
     float dot = x * ddx + y * ddy + z * ddz;

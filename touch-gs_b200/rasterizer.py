@@ -1,0 +1,314 @@
+"""The operator surface: ``GaussianRasterizationSettings`` / ``GaussianRasterizer`` /
+``rasterize_gaussians`` -> ``_RasterizeGaussians`` (a ``torch.autograd.Function``).
+
+Mirrors the Inria-style operator the Touch-GS trainer calls once per step
+(``ns-train depth-gaussian-splatting``, reference ``scripts/train_bunny_real.sh:52``; the
+rasterizer itself is not vendored in the reference -- SURVEY.md §0, §8(b)), extended with
+
+* rendered expected depth and alpha (one traversal with RGB), and
+* the touch-depth loss whose gradient is FUSED into the backward kernel: pass
+  ``touch_depth`` (metres, 0 = invalid: reference ``utils/fuse_touch_vision.py:372-388``),
+  ``touch_weight`` (e.g. 1/sigma from the uncertainty PNG, reference
+  ``utils/fuse_touch_vision.py:376,387``), ``depth_loss in {'none','l1','l2'}`` and
+  ``depth_loss_mult`` (reference ``scripts/train_block_data.sh:50``: ``--pipeline.model.depth-loss-mult``).
+  The caller must NOT add that loss term to its autograd graph again; ``depth_residual`` is returned
+  (non-differentiable) so the loss value can still be logged.
+
+All compute happens in ``libtgs.so`` (hand-written sm_100a CUDA, C ABI in ``include/tgs.h``).
+PyTorch is used for device memory, streams and ``torch.distributed`` only.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+TILE = 16
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor      # [4,4] transposed world->view
+    projmatrix: torch.Tensor      # [4,4] transposed full projection
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool = False
+    debug: bool = False
+
+
+class TouchOptions(NamedTuple):
+    """Keyword-only extension of the operator (default = off: the base call is unchanged)."""
+    touch_depth: Optional[torch.Tensor] = None     # [H,W]
+    touch_weight: Optional[torch.Tensor] = None    # [H,W]
+    depth_loss: str = "none"                       # 'none' | 'l1' | 'l2'
+    depth_loss_mult: float = 1.0
+    depth_normalize: bool = True                   # returned depth = D/alpha
+    depth_loss_norm: Optional[float] = None        # Z; None -> #(touch_depth > 0)
+    tile_rows: Optional[Tuple[int, int]] = None    # tile-row band of this rank
+    process_group: object = None                   # all-reduce group for the screen-space gradients
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _chk(t: Optional[torch.Tensor], name: str, shape, device, dtype=torch.float32):
+    if t is None:
+        return None
+    if t.device != device:
+        raise ValueError(f"{name} must be on {device}, got {t.device}")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    if shape is not None:
+        if t.dim() != len(shape) or any(s is not None and int(t.shape[i]) != s for i, s in enumerate(shape)):
+            raise ValueError(f"{name} must have shape {list(shape)}, got {list(t.shape)}")
+    return t.contiguous()
+
+
+class _Scratch:
+    """Allocator handed to the C ABI: the three saved byte buffers are torch tensors, so they come
+    from torch's caching allocator on the caller's device and are kept alive by ``ctx``."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+        self.error = None
+        self.cb = L.ALLOC_FN(self._alloc)
+
+    def _alloc(self, _user, which, nbytes):
+        try:
+            t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            self.bufs[int(which)] = t
+            return t.data_ptr()
+        except Exception as e:  # noqa: BLE001 - must not propagate through the C frame
+            self.error = e
+            return None
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _make_settings(rs: GaussianRasterizationSettings, opt: TouchOptions, K: int, keep):
+    dev = rs.viewmatrix.device
+    vm = _chk(rs.viewmatrix, "viewmatrix", (4, 4), dev)
+    pmx = _chk(rs.projmatrix, "projmatrix", (4, 4), dev)
+    cam = _chk(rs.campos.reshape(-1), "campos", (3,), dev)
+    bg = _chk(rs.bg.reshape(-1), "bg", (3,), dev)
+    keep.extend([vm, pmx, cam, bg])
+    Ty = (rs.image_height + TILE - 1) // TILE
+    r0, r1 = (0, Ty) if opt.tile_rows is None else (int(opt.tile_rows[0]), int(opt.tile_rows[1]))
+    if not (0 <= r0 <= r1 <= Ty):
+        raise ValueError(f"tile_rows {opt.tile_rows} outside [0, {Ty}]")
+    s = L.TgsSettings(
+        image_width=int(rs.image_width), image_height=int(rs.image_height),
+        tanfovx=float(rs.tanfovx), tanfovy=float(rs.tanfovy), scale_modifier=float(rs.scale_modifier),
+        sh_degree=int(rs.sh_degree), sh_coeffs=int(K), prefiltered=int(bool(rs.prefiltered)),
+        debug=int(bool(rs.debug)), tile_row_begin=r0, tile_row_end=r1,
+        depth_normalize=int(bool(opt.depth_normalize)),
+        viewmatrix=vm.data_ptr(), projmatrix=pmx.data_ptr(), campos=cam.data_ptr(), bg=bg.data_ptr())
+    return s, (r0, r1, Ty)
+
+
+def _make_gaussians(means3D, opacities, sh, colors, scales, rots, cov3D):
+    return L.TgsGaussians(
+        N=int(means3D.shape[0]), means3D=means3D.data_ptr(), opacities=opacities.data_ptr(),
+        shs=None if sh is None else sh.data_ptr(),
+        colors_precomp=None if colors is None else colors.data_ptr(),
+        scales=None if scales is None else scales.data_ptr(),
+        rotations=None if rots is None else rots.data_ptr(),
+        cov3D_precomp=None if cov3D is None else cov3D.data_ptr())
+
+
+def _empty_if(t):
+    return None if (t is None or t.numel() == 0) else t
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                cov3Ds_precomp, raster_settings, opt):
+        lib = L.load()
+        rs: GaussianRasterizationSettings = raster_settings
+        opt = opt if opt is not None else TouchOptions()
+        if opt.depth_loss not in L.LOSS_MODES:
+            raise ValueError(f"depth_loss must be one of {list(L.LOSS_MODES)}, got {opt.depth_loss!r}")
+        dev = means3D.device
+        if dev.type != "cuda":
+            raise RuntimeError("touchgs_b200 rasterizer is CUDA-only (no CPU fallback); tensors are on " + str(dev))
+        sh, colors_precomp = _empty_if(sh), _empty_if(colors_precomp)
+        scales, rotations, cov3Ds_precomp = _empty_if(scales), _empty_if(rotations), _empty_if(cov3Ds_precomp)
+        N = int(means3D.shape[0])
+        H, W = int(rs.image_height), int(rs.image_width)
+        means3D = _chk(means3D, "means3D", (N, 3), dev)
+        opacities = _chk(opacities.reshape(-1), "opacities", (N,), dev)
+        K = 0
+        if sh is not None:
+            if sh.dim() != 3 or sh.shape[0] != N or sh.shape[2] != 3:
+                raise ValueError(f"shs must have shape [N,K,3], got {list(sh.shape)}")
+            K = int(sh.shape[1])
+            sh = _chk(sh, "shs", (N, K, 3), dev)
+        colors_precomp = _chk(colors_precomp, "colors_precomp", (N, 3), dev)
+        scales = _chk(scales, "scales", (N, 3), dev)
+        rotations = _chk(rotations, "rotations", (N, 4), dev)
+        cov3Ds_precomp = _chk(cov3Ds_precomp, "cov3D_precomp", (N, 6), dev)
+        touch_depth = _chk(opt.touch_depth, "touch_depth", None, dev)
+        touch_weight = _chk(opt.touch_weight, "touch_weight", None, dev)
+        for nm, t in (("touch_depth", touch_depth), ("touch_weight", touch_weight)):
+            if t is not None and t.numel() != H * W:
+                raise ValueError(f"{nm} must have H*W = {H * W} elements, got {list(t.shape)}")
+        if opt.depth_loss != "none" and touch_depth is None:
+            raise ValueError("depth_loss != 'none' requires touch_depth")
+
+        keep = []
+        with torch.cuda.device(dev):
+            s, (r0, r1, Ty) = _make_settings(rs, opt, K, keep)
+            g = _make_gaussians(means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp)
+            full = (r0 == 0 and r1 == Ty)
+            mk = torch.empty if full else torch.zeros
+            color = mk((3, H, W), dtype=torch.float32, device=dev)
+            depth = mk((1, H, W), dtype=torch.float32, device=dev)
+            alpha = mk((1, H, W), dtype=torch.float32, device=dev)
+            resid = torch.zeros((1, H, W), dtype=torch.float32, device=dev) if (touch_depth is None or not full) \
+                else torch.empty((1, H, W), dtype=torch.float32, device=dev)
+            radii = torch.zeros((N,), dtype=torch.int32, device=dev)
+            scratch = _Scratch(dev)
+            saved = L.TgsSaved()
+            rc = lib.tgs_forward(C.byref(s), C.byref(g), scratch.cb, None, _ptr(color), _ptr(depth), _ptr(alpha),
+                                 _ptr(radii), _ptr(touch_depth), _ptr(resid) if touch_depth is not None else None,
+                                 C.byref(saved), _stream_ptr(dev))
+            if scratch.error is not None:
+                raise scratch.error
+            L.check(rc, "tgs_forward")
+
+        ctx.rs, ctx.opt, ctx.K = rs, opt, K
+        ctx.num_rendered = int(saved.num_rendered)
+        ctx.has = (sh is not None, colors_precomp is not None, scales is not None, cov3Ds_precomp is not None)
+        ctx.touch = (touch_depth, touch_weight)
+        none = torch.empty(0, device=dev)
+        ctx.save_for_backward(means3D, opacities, sh if sh is not None else none,
+                              colors_precomp if colors_precomp is not None else none,
+                              scales if scales is not None else none,
+                              rotations if rotations is not None else none,
+                              cov3Ds_precomp if cov3Ds_precomp is not None else none,
+                              radii, scratch.bufs[L.BUF_GEOM], scratch.bufs[L.BUF_BINNING], scratch.bufs[L.BUF_IMAGE])
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(radii, resid)
+        return color, radii, depth, alpha, resid
+
+    @staticmethod
+    def backward(ctx, g_color, _g_radii, g_depth, g_alpha, _g_resid):
+        lib = L.load()
+        (means3D, opacities, sh, colors, scales, rots, cov3D, radii, geom, binning, image) = ctx.saved_tensors
+        has_sh, has_col, has_sr, has_cov = ctx.has
+        sh = sh if has_sh else None
+        colors = colors if has_col else None
+        scales, rots = (scales, rots) if has_sr else (None, None)
+        cov3D = cov3D if has_cov else None
+        rs, opt, K = ctx.rs, ctx.opt, ctx.K
+        dev = means3D.device
+        N = int(means3D.shape[0])
+        H, W = int(rs.image_height), int(rs.image_width)
+        keep = []
+        with torch.cuda.device(dev):
+            s, _ = _make_settings(rs, opt, K, keep)
+            g = _make_gaussians(means3D, opacities, sh, colors, scales, rots, cov3D)
+            saved = L.TgsSaved(geom=geom.data_ptr(), binning=binning.data_ptr(), image=image.data_ptr(),
+                               num_rendered=ctx.num_rendered)
+            g_color = torch.zeros((3, H, W), dtype=torch.float32, device=dev) if g_color is None \
+                else _chk(g_color, "grad_color", (3, H, W), dev)
+            g_depth = None if g_depth is None else _chk(g_depth.reshape(H, W), "grad_depth", (H, W), dev)
+            g_alpha = None if g_alpha is None else _chk(g_alpha.reshape(H, W), "grad_alpha", (H, W), dev)
+            touch_depth, touch_weight = ctx.touch
+            touch = None
+            if touch_depth is not None and opt.depth_loss != "none":
+                scale = torch.empty(2, dtype=torch.float32, device=dev)
+                norm = float(opt.depth_loss_norm) if opt.depth_loss_norm is not None else 0.0
+                L.check(lib.tgs_touch_loss_scale(_ptr(touch_depth), H * W, float(opt.depth_loss_mult), norm,
+                                                 _ptr(scale), _stream_ptr(dev)), "tgs_touch_loss_scale")
+                keep.append(scale)
+                touch = L.TgsTouch(target=touch_depth.data_ptr(),
+                                   weight=None if touch_weight is None else touch_weight.data_ptr(),
+                                   scale=scale.data_ptr(), mode=L.LOSS_MODES[opt.depth_loss])
+            sgrad = torch.empty((max(N, 1), L.NGRAD), dtype=torch.float32, device=dev)
+            L.check(lib.tgs_backward_render(C.byref(s), C.byref(g), C.byref(saved), _ptr(g_color), _ptr(g_depth),
+                                            _ptr(g_alpha), None if touch is None else C.byref(touch), None,
+                                            _ptr(sgrad), _stream_ptr(dev)), "tgs_backward_render")
+            if opt.process_group is not None:
+                # the ONE exchange step of the multi-GPU path: sum the compact [N,10] screen-space
+                # gradients of all tile-row bands, NCCL over NVLink
+                import torch.distributed as dist
+                dist.all_reduce(sgrad, op=dist.ReduceOp.SUM, group=opt.process_group)
+            dmeans2D = torch.empty((N, 3), dtype=torch.float32, device=dev)
+            dmeans3D = torch.empty((N, 3), dtype=torch.float32, device=dev)
+            dopac = torch.empty((N,), dtype=torch.float32, device=dev)
+            dsh = torch.empty((N, K, 3), dtype=torch.float32, device=dev) if has_sh else None
+            dcol = torch.empty((N, 3), dtype=torch.float32, device=dev) if has_col else None
+            dsc = torch.empty((N, 3), dtype=torch.float32, device=dev) if has_sr else None
+            drot = torch.empty((N, 4), dtype=torch.float32, device=dev) if has_sr else None
+            dcov = torch.empty((N, 6), dtype=torch.float32, device=dev) if has_cov else None
+            gr = L.TgsGrads(dmeans2D=dmeans2D.data_ptr(), dmeans3D=dmeans3D.data_ptr(), dopacity=dopac.data_ptr(),
+                            dshs=None if dsh is None else dsh.data_ptr(),
+                            dcolors=None if dcol is None else dcol.data_ptr(),
+                            dscales=None if dsc is None else dsc.data_ptr(),
+                            drotations=None if drot is None else drot.data_ptr(),
+                            dcov3D=None if dcov is None else dcov.data_ptr())
+            L.check(lib.tgs_backward_preprocess(C.byref(s), C.byref(g), C.byref(saved), _ptr(radii), _ptr(sgrad),
+                                                C.byref(gr), _stream_ptr(dev)), "tgs_backward_preprocess")
+        ctx.screen_grads = None
+        return (dmeans3D, dmeans2D, dsh, dcol, dopac.reshape(-1, 1), dsc, drot, dcov, None, None)
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                        cov3Ds_precomp, raster_settings, touch: Optional[TouchOptions] = None):
+    """Same positional signature as the reference-era ``rasterize_gaussians`` plus the
+    optional ``touch`` extension.  Returns (color [3,H,W], radii [N] int32, depth [1,H,W],
+    alpha [1,H,W], depth_residual [1,H,W])."""
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings, touch)
+
+
+class GaussianRasterizer(torch.nn.Module):
+    def __init__(self, raster_settings: GaussianRasterizationSettings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions: torch.Tensor) -> torch.Tensor:
+        """bool[N]: view-space z > 0.2 for the module's camera."""
+        lib = L.load()
+        rs = self.raster_settings
+        dev = positions.device
+        if dev.type != "cuda":
+            raise RuntimeError("touchgs_b200 rasterizer is CUDA-only (no CPU fallback)")
+        with torch.no_grad(), torch.cuda.device(dev):
+            N = int(positions.shape[0])
+            pos = _chk(positions.detach(), "positions", (N, 3), dev)
+            vm = _chk(rs.viewmatrix, "viewmatrix", (4, 4), dev)
+            out = torch.zeros((N,), dtype=torch.uint8, device=dev)
+            L.check(lib.tgs_mark_visible(N, _ptr(pos), _ptr(vm), _ptr(out), _stream_ptr(dev)), "tgs_mark_visible")
+        return out.bool()
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
+                rotations=None, cov3D_precomp=None, *, touch_depth=None, touch_weight=None,
+                depth_loss: str = "none", depth_loss_mult: float = 1.0, depth_normalize: bool = True,
+                depth_loss_norm: Optional[float] = None, tile_rows=None, process_group=None):
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        e = torch.Tensor([]).to(means3D.device)
+        opt = TouchOptions(touch_depth, touch_weight, depth_loss, depth_loss_mult, depth_normalize,
+                           depth_loss_norm, tile_rows, process_group)
+        return rasterize_gaussians(means3D, means2D,
+                                   e if shs is None else shs, e if colors_precomp is None else colors_precomp,
+                                   opacities, e if scales is None else scales, e if rotations is None else rotations,
+                                   e if cov3D_precomp is None else cov3D_precomp, self.raster_settings, opt)
