@@ -149,6 +149,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         N = int(means3D.shape[0])
         H, W = int(rs.image_height), int(rs.image_width)
         means3D = _chk(means3D, "means3D", (N, 3), dev)
+        opacity_shape = tuple(opacities.shape)
         opacities = _chk(opacities.reshape(-1), "opacities", (N,), dev)
         K = 0
         if sh is not None:
@@ -190,6 +191,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             L.check(rc, "tgs_forward")
 
         ctx.rs, ctx.opt, ctx.K = rs, opt, K
+        ctx.opacity_shape = opacity_shape
         ctx.num_rendered = int(saved.num_rendered)
         ctx.has = (sh is not None, colors_precomp is not None, scales is not None, cov3Ds_precomp is not None)
         ctx.touch = (touch_depth, touch_weight)
@@ -263,8 +265,10 @@ class _RasterizeGaussians(torch.autograd.Function):
                             dcov3D=None if dcov is None else dcov.data_ptr())
             L.check(lib.tgs_backward_preprocess(C.byref(s), C.byref(g), C.byref(saved), _ptr(radii), _ptr(sgrad),
                                                 C.byref(gr), _stream_ptr(dev)), "tgs_backward_preprocess")
-        ctx.screen_grads = None
-        return (dmeans3D, dmeans2D, dsh, dcol, dopac.reshape(-1, 1), dsc, drot, dcov, None, None)
+        # autograd rejects a gradient for an input that was not a Variable (e.g. means2D=None)
+        grads = (dmeans3D, dmeans2D, dsh, dcol, dopac.reshape(ctx.opacity_shape), dsc, drot, dcov)
+        need = ctx.needs_input_grad
+        return tuple(g if need[i] else None for i, g in enumerate(grads)) + (None, None)
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
