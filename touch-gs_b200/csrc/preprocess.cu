@@ -85,7 +85,8 @@ k_preprocess(int N, const float* __restrict__ means, const float* __restrict__ s
     TgsRecord r;
     r.a = make_float4(p.px, p.py, p.depth, __int_as_float(i));
     r.b = make_float4(p.conA, p.conB, p.conC, vis ? opac[i] : 0.0f);
-    r.c = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
+    // c.w = power threshold of the alpha >= 1/255 test: o*exp(power) >= 1/255  <=>  power >= -ln(255 o)
+    r.c = make_float4(rgb[0], rgb[1], rgb[2], vis ? -logf(255.0f * opac[i]) : 3.0e38f);
     rec[i] = r;
 #pragma unroll
     for (int k = 0; k < 6; ++k) cov3D[6 * i + k] = cov[k];

@@ -7,6 +7,11 @@
 //     each batch of 256 records (12 KB) is brought into shared memory by ONE TMA bulk copy
 //     (cp.async.bulk ... mbarrier::complete_tx::bytes), double-buffered: the copy of batch b+2 is
 //     issued as soon as batch b has been consumed, so HBM/L2 latency is hidden behind the blend;
+//   * EXACT warp-level culling: each lane tests one splat's alpha-threshold ellipse against the warp's
+//     8x4 pixel patch (closed-form minimum of the quadratic over the rectangle), a ballot gives the
+//     survivors, and only those are evaluated per pixel -- most (pixel, splat) pairs of the 3-sigma
+//     square bounding boxes never reach alpha >= 1/255, so this removes the bulk of the arithmetic
+//     while leaving every result bit-identical;
 //   * forward: RGB, expected depth and alpha are composited in ONE traversal;
 //   * backward: back-to-front replay; the per-pixel depth / alpha gradients are computed IN-KERNEL
 //     from the touch target, its weight and the loss scale (no autograd round trip through HBM);
@@ -76,17 +81,56 @@ __device__ __forceinline__ float splat_alpha(float opacity, float G) {
 
 struct PixelMap {
     int px, py, pix; bool inside; float fx, fy;
+    float x0, x1, y0, y1;           // pixel-centre rectangle of this warp's 8x4 patch
 };
 __device__ __forceinline__ PixelMap map_pixel(int tile, int Tx, int W, int H) {
     PixelMap m;
     int tx = tile % Tx, ty = tile / Tx;
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    m.px = tx * TGS_TILE + (warp & 1) * 8 + (lane & 7);
-    m.py = ty * TGS_TILE + (warp >> 1) * 4 + (lane >> 3);
+    int wx = tx * TGS_TILE + (warp & 1) * 8, wy = ty * TGS_TILE + (warp >> 1) * 4;
+    m.px = wx + (lane & 7);
+    m.py = wy + (lane >> 3);
     m.inside = (m.px < W) && (m.py < H);
     m.pix = m.py * W + m.px;
     m.fx = (float)m.px; m.fy = (float)m.py;
+    m.x0 = (float)wx; m.x1 = (float)(wx + 7); m.y0 = (float)wy; m.y1 = (float)(wy + 3);
     return m;
+}
+
+// EXACT warp-level cull.  A splat can only contribute to a pixel if alpha = o*exp(power) >= 1/255,
+// i.e. power >= thr := -ln(255 o)  (thr is precomputed per splat in record.c.w).  power = -q/2 with
+// q(p) = (p-mu)^T Q (p-mu) convex, so over the warp's pixel rectangle R the maximum power is -q_min/2
+// where q_min is 0 if mu lies in R and otherwise the minimum over the four edges (each a clamped 1-D
+// quadratic).  If even that maximum is below thr (minus a safety margin that dominates the fp32
+// rounding of this bound and of the per-pixel evaluation), NO pixel of the patch would pass the
+// alpha test, so skipping the splat for the whole warp is bit-identical to evaluating it.
+__device__ __forceinline__ bool patch_may_touch(const float4 a, const float4 q, float thr, const PixelMap& pm) {
+    const float ex0 = pm.x0 - a.x, ex1 = pm.x1 - a.x, ey0 = pm.y0 - a.y, ey1 = pm.y1 - a.y;
+    if (ex0 <= 0.0f && ex1 >= 0.0f && ey0 <= 0.0f && ey1 >= 0.0f) return thr <= 0.05f;
+    const float A = q.x, B = q.y, Cc = q.z;
+    const float rA = __fdividef(1.0f, A), rC = __fdividef(1.0f, Cc);
+    float qmin, tmax;
+    {   // vertical edges: dx fixed, dy* = clamp(-B dx / C)
+        float dy = fminf(fmaxf(-B * ex0 * rC, ey0), ey1);
+        float t1 = A * ex0 * ex0, t2 = Cc * dy * dy, t3 = 2.0f * B * ex0 * dy;
+        qmin = t1 + t2 + t3; tmax = t1 + t2 + fabsf(t3);
+        dy = fminf(fmaxf(-B * ex1 * rC, ey0), ey1);
+        t1 = A * ex1 * ex1; t2 = Cc * dy * dy; t3 = 2.0f * B * ex1 * dy;
+        float qq = t1 + t2 + t3;
+        if (qq < qmin) { qmin = qq; tmax = t1 + t2 + fabsf(t3); }
+    }
+    {   // horizontal edges: dy fixed, dx* = clamp(-B dy / A)
+        float dx = fminf(fmaxf(-B * ey0 * rA, ex0), ex1);
+        float t1 = A * dx * dx, t2 = Cc * ey0 * ey0, t3 = 2.0f * B * dx * ey0;
+        float qq = t1 + t2 + t3;
+        if (qq < qmin) { qmin = qq; tmax = t1 + t2 + fabsf(t3); }
+        dx = fminf(fmaxf(-B * ey1 * rA, ex0), ex1);
+        t1 = A * dx * dx; t2 = Cc * ey1 * ey1; t3 = 2.0f * B * dx * ey1;
+        qq = t1 + t2 + t3;
+        if (qq < qmin) { qmin = qq; tmax = t1 + t2 + fabsf(t3); }
+    }
+    const float margin = 0.05f + 1e-5f * tmax;
+    return -0.5f * qmin >= thr - margin;
 }
 
 // ------------------------------------------------------------------------------- forward
@@ -98,7 +142,7 @@ k_render_fwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
              const float* __restrict__ t_target, float* __restrict__ residual) {
     __shared__ __align__(128) float4 sbuf[2][kBatch * 3];
     __shared__ __align__(8) uint64_t full[2];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int tile = blockIdx.x + row0 * Tx;
     const PixelMap pm = map_pixel(tile, Tx, W, H);
     const uint2 rng = ranges[tile];
@@ -121,23 +165,32 @@ k_render_fwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
     int b = 0;
     for (; b < nb; ++b) {
         mbar_wait(&full[b & 1], (uint32_t)((b >> 1) & 1));
-        if (!done) {
-            const float4* s = sbuf[b & 1];
-            const int cnt = min(kBatch, len - b * kBatch);
-            for (int j = 0; j < cnt; ++j) {
+        const float4* s = sbuf[b & 1];
+        const int cnt = min(kBatch, len - b * kBatch);
+        for (int c0 = 0; c0 < cnt; c0 += 32) {
+            if (__all_sync(kFull, done)) break;                 // whole warp saturated
+            const int jl = c0 + lane;
+            bool pass = false;
+            if (jl < cnt) pass = patch_may_touch(s[3 * jl], s[3 * jl + 1], s[3 * jl + 2].w, pm);
+            unsigned mask = __ballot_sync(kFull, pass);
+            while (mask) {
+                const int j = c0 + __ffs(mask) - 1;
+                mask &= mask - 1;
                 const float4 a = s[3 * j], q = s[3 * j + 1];
                 const float dx = a.x - pm.fx, dy = a.y - pm.fy;
                 const float power = splat_power(q, dx, dy);
-                if (power > 0.0f) continue;
                 const float alpha = splat_alpha(q.w, __expf(power));
-                if (alpha < TGS_ALPHA_MIN) continue;
+                bool valid = !done && (power <= 0.0f) && (alpha >= TGS_ALPHA_MIN);
+                if (!__any_sync(kFull, valid)) continue;
                 const float test_T = T * (1.0f - alpha);
-                if (test_T < TGS_T_EPS) { done = true; break; }
-                const float4 c = s[3 * j + 2];
-                const float w = alpha * T;
-                C0 += c.x * w; C1 += c.y * w; C2 += c.z * w; D += a.z * w;
-                T = test_T;
-                last = (uint32_t)(b * kBatch + j + 1);
+                if (valid && test_T < TGS_T_EPS) { done = true; valid = false; }
+                if (valid) {
+                    const float4 c = s[3 * j + 2];
+                    const float w = alpha * T;
+                    C0 += c.x * w; C1 += c.y * w; C2 += c.z * w; D += a.z * w;
+                    T = test_T;
+                    last = (uint32_t)(b * kBatch + j + 1);
+                }
             }
         }
         const int nd = __syncthreads_count(done);
@@ -249,11 +302,11 @@ k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
     // colour: d(T_final*bg)/dalpha_i = -T_final/(1-alpha_i) * bg ; alpha: dA/dalpha_i = +T_final/(1-alpha_i)
     const float tail = Tf * (gA - bgdot);
 
-    // ---- nothing beyond the deepest contributor of any pixel of the tile needs replaying
-    uint32_t m = nc;
+    // ---- nothing beyond the deepest contributor of any pixel needs replaying (tile- and warp-level)
+    uint32_t wmax = nc;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(kFull, m, o));
-    if (lane == 0) s_max[warp] = m;
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(kFull, wmax, o));
+    if (lane == 0) s_max[warp] = wmax;
     if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
     __syncthreads();
     uint32_t mx = s_max[0];
@@ -282,45 +335,57 @@ k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
         const int b = nb - 1 - q;
         const int cnt = min(kBatch, leff - b * kBatch);
         const float4* s = sbuf[q & 1];
-        for (int j = cnt - 1; j >= 0; --j) {
-            const uint32_t idx = (uint32_t)(b * kBatch + j);
-            const float4 a = s[3 * j], cq = s[3 * j + 1];
-            const float dx = a.x - pm.fx, dy = a.y - pm.fy;
-            const float power = splat_power(cq, dx, dy);
-            const float G = __expf(power);
-            const float alpha = splat_alpha(cq.w, G);
-            const bool valid = (idx < nc) && (power <= 0.0f) && (alpha >= TGS_ALPHA_MIN);
-            if (!__any_sync(kFull, valid)) continue;
-            float v[TGS_NGRAD];
+        const int base = b * kBatch;
+        for (int c0 = ((cnt - 1) >> 5) << 5; c0 >= 0; c0 -= 32) {
+            if ((uint32_t)(base + c0) >= wmax) continue;        // beyond this warp's deepest contributor
+            const int jl = c0 + lane;
+            bool pass = false;
+            if (jl < cnt && (uint32_t)(base + jl) < wmax)
+                pass = patch_may_touch(s[3 * jl], s[3 * jl + 1], s[3 * jl + 2].w, pm);
+            unsigned mask = __ballot_sync(kFull, pass);
+            while (mask) {
+                const int hb = 31 - __clz(mask);
+                mask &= ~(1u << hb);
+                const int j = c0 + hb;
+                const uint32_t idx = (uint32_t)(base + j);
+                const float4 a = s[3 * j], cq = s[3 * j + 1];
+                const float dx = a.x - pm.fx, dy = a.y - pm.fy;
+                const float power = splat_power(cq, dx, dy);
+                const float G = __expf(power);
+                const float alpha = splat_alpha(cq.w, G);
+                const bool valid = (idx < nc) && (power <= 0.0f) && (alpha >= TGS_ALPHA_MIN);
+                if (!__any_sync(kFull, valid)) continue;
+                float v[TGS_NGRAD];
 #pragma unroll
-            for (int k = 0; k < TGS_NGRAD; ++k) v[k] = 0.0f;
-            if (valid) {
-                const float4 c = s[3 * j + 2];
-                const float inv = 1.0f / (1.0f - alpha);
-                T = T * inv;                               // transmittance in front of this splat
-                const float w = alpha * T;
-                const float om = 1.0f - last_alpha;
-                ac0 = last_alpha * lc0 + om * ac0; lc0 = c.x;
-                ac1 = last_alpha * lc1 + om * ac1; lc1 = c.y;
-                ac2 = last_alpha * lc2 + om * ac2; lc2 = c.z;
-                acD = last_alpha * lcD + om * acD; lcD = a.z;
-                float dLda = (c.x - ac0) * g0 + (c.y - ac1) * g1 + (c.z - ac2) * g2 + (a.z - acD) * gD;
-                dLda = dLda * T + tail * inv;
-                last_alpha = alpha;
-                const float dLdG = cq.w * dLda;
-                const float gdx = G * dx, gdy = G * dy;
-                v[0] = dLdG * (-gdx * cq.x - gdy * cq.y);
-                v[1] = dLdG * (-gdy * cq.z - gdx * cq.y);
-                v[2] = -0.5f * gdx * dx * dLdG;
-                v[3] = -gdx * dy * dLdG;
-                v[4] = -0.5f * gdy * dy * dLdG;
-                v[5] = G * dLda;
-                v[6] = w * g0; v[7] = w * g1; v[8] = w * g2;
-                v[9] = w * gD;
+                for (int k = 0; k < TGS_NGRAD; ++k) v[k] = 0.0f;
+                if (valid) {
+                    const float4 c = s[3 * j + 2];
+                    const float inv = 1.0f / (1.0f - alpha);
+                    T = T * inv;                               // transmittance in front of this splat
+                    const float w = alpha * T;
+                    const float om = 1.0f - last_alpha;
+                    ac0 = last_alpha * lc0 + om * ac0; lc0 = c.x;
+                    ac1 = last_alpha * lc1 + om * ac1; lc1 = c.y;
+                    ac2 = last_alpha * lc2 + om * ac2; lc2 = c.z;
+                    acD = last_alpha * lcD + om * acD; lcD = a.z;
+                    float dLda = (c.x - ac0) * g0 + (c.y - ac1) * g1 + (c.z - ac2) * g2 + (a.z - acD) * gD;
+                    dLda = dLda * T + tail * inv;
+                    last_alpha = alpha;
+                    const float dLdG = cq.w * dLda;
+                    const float gdx = G * dx, gdy = G * dy;
+                    v[0] = dLdG * (-gdx * cq.x - gdy * cq.y);
+                    v[1] = dLdG * (-gdy * cq.z - gdx * cq.y);
+                    v[2] = -0.5f * gdx * dx * dLdG;
+                    v[3] = -gdx * dy * dLdG;
+                    v[4] = -0.5f * gdy * dy * dLdG;
+                    v[5] = G * dLda;
+                    v[6] = w * g0; v[7] = w * g1; v[8] = w * g2;
+                    v[9] = w * gD;
+                }
+                float sum; int slot; bool ok;
+                warp_reduce_scatter10(v, lane, sum, slot, ok);
+                if (ok) atomicAdd(sgrad + (size_t)__float_as_int(a.w) * TGS_NGRAD + slot, sum);
             }
-            float sum; int slot; bool ok;
-            warp_reduce_scatter10(v, lane, sum, slot, ok);
-            if (ok) atomicAdd(sgrad + (size_t)__float_as_int(a.w) * TGS_NGRAD + slot, sum);
         }
         __syncthreads();
         if (tid == 0 && q + 2 < nb) issue(q + 2);

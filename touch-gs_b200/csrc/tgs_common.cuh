@@ -13,7 +13,7 @@
 // into shared memory by a single TMA bulk copy (cp.async.bulk) per batch.
 //   a = (x_pix, y_pix, depth, bits(gaussian id))
 //   b = (conic A, conic B, conic C, opacity)
-//   c = (r, g, b, unused)
+//   c = (r, g, b, thr)   thr = -ln(255*opacity): power threshold of the alpha >= 1/255 test
 struct __align__(16) TgsRecord { float4 a, b, c; };
 static_assert(sizeof(TgsRecord) == 48, "record must be 48 bytes");
 
