@@ -37,7 +37,7 @@ DEPTH_LOSS_MULT = 0.2       # reference scripts/train_block_data.sh:50 (--pipeli
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c5"])
@@ -60,7 +60,9 @@ def peaks():
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md).
+    The sampler process is started BEFORE warm-up (its NVML initialisation stalls the driver for tens
+    of milliseconds, which must not land inside a timed window); samples are windowed by wall clock."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -75,25 +77,37 @@ class ClockSampler:
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 3.0:      # wait until NVML is up
+                time.sleep(0.02)
         except Exception:  # noqa: BLE001
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:  # noqa: BLE001
             self.proc.kill()
+
+    def summary(self, t_begin, t_end, t_warm):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        window = "timed region"
+        rows = [l for t, l in self.lines if t_begin <= t <= t_end + 0.11]
+        if not rows:        # timed region shorter than the polling period: use everything since warm-up began
+            rows = [l for t, l in self.lines if t_warm <= t <= t_end + 0.11]
+            window = "warm-up + timed region (timed region shorter than the 100 ms polling period)"
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in rows:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -106,7 +120,8 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": window,
+                "reasons": sorted(reasons)}
 
 
 # --------------------------------------------------------------------------- workload
@@ -176,17 +191,50 @@ class Stepper:
         d = b["dev"]
         return self._run(b["cam"], d["view"], d["proj"], d["campos"], d["gt"], d["target"], d["weight"])
 
-    def e2e_step(self, b):
-        """Per-step inputs (camera, ground-truth image, touch depth + weight) start in PINNED HOST memory;
-        the step's result (loss) is read back to the host."""
-        h = b["host"]
-        if self.stage is None:
-            self.stage = {k: torch.empty_like(v, device=self.dev) for k, v in h.items()}
-        s = self.stage
-        for k, v in h.items():
-            s[k].copy_(v, non_blocking=True)
+    def _prefetch(self, b, slot):
+        """H2D of one step's inputs from pinned host memory on the copy stream."""
+        with torch.cuda.stream(self.copy_stream):
+            for k, v in b["host"].items():
+                self.stage[slot][k].copy_(v, non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+
+    def e2e_begin(self, batches):
+        h = batches[0]["host"]
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.stage = [{k: torch.empty_like(v, device=self.dev) for k, v in h.items()} for _ in range(2)]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        self.loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self.loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        self.batches, self.k, self.losses = batches, 0, []
+        self._prefetch(batches[0], 0)
+
+    def e2e_step(self, i):
+        """End-to-end step i: its inputs (camera, ground-truth image, touch depth + weight) start in
+        PINNED HOST memory and are copied H2D on a copy stream (issued one step ahead, double-buffered);
+        the step's result (loss) is copied D2H into pinned memory and read by the host one step later."""
+        n = len(self.batches)
+        b, slot = self.batches[i % n], self.k & 1
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(self.ready[slot])
+        s = self.stage[slot]
         loss = self._run(b["cam"], s["view"], s["proj"], s["campos"], s["gt"], s["target"], s["weight"])
-        return float(loss.item())           # D2H read of the step result
+        self.loss_host[slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)     # D2H of the result
+        self.loss_ev[slot].record(cur)
+        self.consumed[slot].record(cur)
+        # next step's inputs: H2D into the other slot once the step that used it has finished
+        nslot = slot ^ 1
+        self.copy_stream.wait_event(self.consumed[nslot])
+        self._prefetch(self.batches[(i + 1) % n], nslot)
+        if self.k > 0:                       # host reads the PREVIOUS step's loss (already on its way)
+            self.loss_ev[nslot].synchronize()
+            self.losses.append(float(self.loss_host[nslot]))
+        self.k += 1
+
+    def e2e_finish(self):
+        slot = (self.k - 1) & 1
+        self.loss_ev[slot].synchronize()
+        self.losses.append(float(self.loss_host[slot]))
 
     @staticmethod
     def h2d_bytes(b):
@@ -331,30 +379,35 @@ def main():
     # once so that torch's caching allocator owns blocks of every size before anything is timed
     for b in batches:
         stepper.device_step(b)
-        stepper.e2e_step(b)
 
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, profile=False):
+    def timed(fn, steps, warmup, profile=False, finalize=None):
+        sampler = ClockSampler(local)
+        sampler.start()
+        t_warm = time.time()
         for i in range(warmup):
-            fn(batches[i % len(batches)])
+            fn(i)
         barrier()
         if profile:
             T._lib.profile_enable(True)
             T._lib.profile_read()
         own0, cub0 = T._lib.launch_counts()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sampler = ClockSampler(local)
-        sampler.start()
+        t_begin = time.time()
         e0.record()
         for i in range(steps):
-            fn(batches[(warmup + i) % len(batches)])
+            fn(warmup + i)
+        if finalize is not None:
+            finalize()
         e1.record()
         barrier()
-        clocks = sampler.stop()
+        t_end = time.time()
+        sampler.stop()
+        clocks = sampler.summary(t_begin, t_end, t_warm)
         ms = e0.elapsed_time(e1)
         prof = None
         if profile:
@@ -368,7 +421,8 @@ def main():
         return ms, clocks, prof, (own1 - own0, cub1 - cub0)
 
     steps, warmup = args.steps, max(args.warmup, 3)
-    ms, clocks, prof, (own, cub) = timed(stepper.device_step, steps, warmup, profile=True)
+    ms, clocks, prof, (own, cub) = timed(lambda i: stepper.device_step(batches[i % len(batches)]), steps, warmup,
+                                         profile=True)
     value = N * steps / (ms * 1e-3)
 
     # measured I (num_rendered) of the cameras used: read from a state-inspecting forward (untimed)
@@ -385,12 +439,15 @@ def main():
 
     e2e = None
     if not args.no_e2e:
-        ms_e, _, _, _ = timed(stepper.e2e_step, steps, warmup)
+        stepper.e2e_begin(batches)
+        ms_e, clocks_e, _, _ = timed(stepper.e2e_step, steps, warmup, finalize=stepper.e2e_finish)
         e2e = {"value": N * steps / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e / steps,
+               "losses_read": len(stepper.losses), "clocks": clocks_e,
                "h2d_bytes_per_step": Stepper.h2d_bytes(batches[0]), "d2h_bytes_per_step": 4,
                "what": "GaussianRasterizer fwd + L1 photometric + fused touch depth-L1 bwd; per-step camera, GT image, "
-                       "touch depth and weight copied from pinned host memory; loss read back (Gaussian parameters are "
-                       "resident training state)"}
+                       "touch depth and weight copied H2D from pinned host memory (copy stream, issued one step ahead, "
+                       "double-buffered); loss copied D2H every step and read by the host one step later; Gaussian "
+                       "parameters are resident training state"}
 
     if rank != 0:
         if world > 1:

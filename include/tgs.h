@@ -202,24 +202,30 @@ int tgs_train_step_host(const TgsSettings* s_host, const TgsGaussians* g_host,
 
 /* introspection used by tests: layout of the saved buffers (byte offsets from the base) */
 typedef struct TgsGeomLayout {
-    size_t records;        /* TgsRecord[N]: 3 x float4 = (x,y,depth,id) (A,B,C,opacity) (r,g,b,-) */
-    size_t cov3D;          /* float[N,6] */
-    size_t tiles_touched;  /* uint32[N] */
-    size_t offsets;        /* uint32[N] inclusive scan */
-    size_t clamped;        /* uint8[N] bit c = colour channel c clamped */
-    size_t rect;           /* uint32[N,2]: (rminx | rmaxx<<16, rminy | rmaxy<<16) */
-    size_t scan_temp;
+    size_t records;           /* TgsRecord[N]: 3 x float4 = (x,y,depth,id) (A,B,C,opacity) (r,g,b,thr) */
+    size_t cov3D;             /* float[N,6] */
+    size_t tiles_touched;     /* uint32[N] */
+    size_t offsets;           /* uint32[N] inclusive scan of tiles_touched IN DEPTH ORDER */
+    size_t clamped;           /* uint8[N] bit c = colour channel c clamped */
+    size_t rect;              /* uint32[N,2]: (rminx | rmaxx<<16, rminy | rmaxy<<16) */
+    size_t depth_keys;        /* uint32[N] bits(depth), 0xFFFFFFFF when nothing is emitted */
+    size_t ids;               /* uint32[N] iota */
+    size_t depth_keys_sorted; /* uint32[N] */
+    size_t order;             /* uint32[N] Gaussian ids in ascending (depth, id) order */
+    size_t temp;              /* CUB temp for the depth sort / scan */
+    size_t temp_bytes;
     size_t total;
 } TgsGeomLayout;
 typedef struct TgsBinningLayout {
-    size_t ranges;         /* uint32[T,2] */
-    size_t records;        /* TgsRecord[I], depth-sorted per tile, contiguous */
-    size_t keys_sorted;    /* uint64[I] (tile << 32 | depth bits) */
-    size_t vals_sorted;    /* uint32[I] Gaussian ids */
-    size_t keys_unsorted;  /* uint64[I] */
-    size_t vals_unsorted;  /* uint32[I] */
+    size_t ranges;            /* uint32[T,2] */
+    size_t records;           /* TgsRecord[I], depth-sorted per tile, contiguous */
+    size_t tile_sorted;       /* key_bytes x [I]: tile id of every sorted instance */
+    size_t vals_sorted;       /* uint32[I] Gaussian ids, final order */
+    size_t tile_unsorted;     /* key_bytes x [I] (emission order: depth-major) */
+    size_t vals_unsorted;     /* uint32[I] */
     size_t sort_temp;
     size_t sort_temp_bytes;
+    size_t key_bytes;         /* 2 when T <= 65536, else 4 */
     size_t total;
 } TgsBinningLayout;
 typedef struct TgsImageLayout {

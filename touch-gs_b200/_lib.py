@@ -57,13 +57,14 @@ class TgsGrads(C.Structure):
 
 class TgsGeomLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in
-                ("records", "cov3D", "tiles_touched", "offsets", "clamped", "rect", "scan_temp", "total")]
+                ("records", "cov3D", "tiles_touched", "offsets", "clamped", "rect", "depth_keys", "ids",
+                 "depth_keys_sorted", "order", "temp", "temp_bytes", "total")]
 
 
 class TgsBinningLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in
-                ("ranges", "records", "keys_sorted", "vals_sorted", "keys_unsorted", "vals_unsorted",
-                 "sort_temp", "sort_temp_bytes", "total")]
+                ("ranges", "records", "tile_sorted", "vals_sorted", "tile_unsorted", "vals_unsorted",
+                 "sort_temp", "sort_temp_bytes", "key_bytes", "total")]
 
 
 class TgsImageLayout(C.Structure):

@@ -88,20 +88,25 @@ extern "C" int tgs_geom_layout(int32_t N, TgsGeomLayout* o) {
     o->offsets = c.take(n * sizeof(uint32_t));
     o->clamped = c.take(n);
     o->rect = c.take(n * sizeof(uint2));
-    o->scan_temp = c.take(tgs_scan_temp_bytes(N > 0 ? N : 1));
+    o->depth_keys = c.take(n * sizeof(uint32_t));
+    o->ids = c.take(n * sizeof(uint32_t));
+    o->depth_keys_sorted = c.take(n * sizeof(uint32_t));
+    o->order = c.take(n * sizeof(uint32_t));
+    o->temp_bytes = tgs_depth_sort_temp_bytes(N > 0 ? N : 1);
+    o->temp = c.take(o->temp_bytes);
     o->total = c.off > 0 ? c.off : TGS_ALIGN;
     return 0;
 }
 extern "C" int tgs_binning_layout(int64_t I, int32_t T, TgsBinningLayout* o) {
     Carver c; size_t n = (size_t)(I > 0 ? I : 0);
-    int end_bit = 32 + ceil_log2((uint32_t)(T > 1 ? T : 2));
-    o->ranges = c.take((size_t)T * sizeof(uint2));
+    o->key_bytes = T <= 65536 ? 2 : 4;
+    o->ranges = c.take((size_t)(T > 0 ? T : 1) * sizeof(uint2));
     o->records = c.take(n * sizeof(TgsRecord));
-    o->keys_sorted = c.take(n * sizeof(uint64_t));
+    o->tile_sorted = c.take(n * o->key_bytes);
     o->vals_sorted = c.take(n * sizeof(uint32_t));
-    o->keys_unsorted = c.take(n * sizeof(uint64_t));
+    o->tile_unsorted = c.take(n * o->key_bytes);
     o->vals_unsorted = c.take(n * sizeof(uint32_t));
-    o->sort_temp_bytes = tgs_sort_temp_bytes(I > 0 ? I : 1, end_bit);
+    o->sort_temp_bytes = tgs_tile_sort_temp_bytes(I > 0 ? I : 1, T);
     o->sort_temp = c.take(o->sort_temp_bytes);
     o->total = c.off;
     return 0;
@@ -121,14 +126,17 @@ GeomView tgs_geom_view(void* base, int N) {
     v.records = (TgsRecord*)(b + l.records); v.cov3D = (float*)(b + l.cov3D);
     v.tiles_touched = (uint32_t*)(b + l.tiles_touched); v.offsets = (uint32_t*)(b + l.offsets);
     v.clamped = (uint8_t*)(b + l.clamped); v.rect = (uint2*)(b + l.rect);
+    v.depth_keys = (uint32_t*)(b + l.depth_keys); v.ids = (uint32_t*)(b + l.ids);
+    v.depth_keys_sorted = (uint32_t*)(b + l.depth_keys_sorted); v.order = (uint32_t*)(b + l.order);
+    v.temp = b + l.temp; v.temp_bytes = l.temp_bytes;
     return v;
 }
 BinView tgs_bin_view(void* base, int64_t I, int T) {
     TgsBinningLayout l; tgs_binning_layout(I, T, &l);
     char* b = (char*)base; BinView v;
     v.ranges = (uint2*)(b + l.ranges); v.records = (TgsRecord*)(b + l.records);
-    v.keys_sorted = (uint64_t*)(b + l.keys_sorted); v.vals_sorted = (uint32_t*)(b + l.vals_sorted);
-    v.keys_unsorted = (uint64_t*)(b + l.keys_unsorted); v.vals_unsorted = (uint32_t*)(b + l.vals_unsorted);
+    v.tile_sorted = b + l.tile_sorted; v.vals_sorted = (uint32_t*)(b + l.vals_sorted);
+    v.tile_unsorted = b + l.tile_unsorted; v.vals_unsorted = (uint32_t*)(b + l.vals_unsorted);
     v.cub_temp = b + l.sort_temp; v.cub_temp_bytes = l.sort_temp_bytes;
     return v;
 }
@@ -207,7 +215,7 @@ extern "C" int tgs_forward(const TgsSettings* s, const TgsGaussians* g, tgs_allo
     int64_t I = 0;
     if (N > 0) {
         rc = tgs_launch_preprocess(cam, s, g, gv, radii, st); if (rc) return rc;
-        rc = tgs_scan_tiles(gv, N, (char*)geom + gl.scan_temp, tgs_scan_temp_bytes(N), st); if (rc) return rc;
+        rc = tgs_depth_order_and_scan(gv, N, st); if (rc) return rc;
         uint32_t* hp = pinned_word();
         if (!hp) { tgs_set_error("cudaHostAlloc failed"); return TGS_ENOMEM; }
         TGS_CUDA(cudaMemcpyAsync(hp, gv.offsets + (N - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -218,13 +226,7 @@ extern "C" int tgs_forward(const TgsSettings* s, const TgsGaussians* g, tgs_allo
     void* binning = alloc(user, TGS_BUF_BINNING, bl.total);
     if (!binning) { tgs_set_error("allocator returned NULL"); return TGS_ENOMEM; }
     BinView bv = tgs_bin_view(binning, I, T);
-    if (I > 0) {
-        rc = tgs_launch_duplicate(gv, N, cam.Tx, bv, st); if (rc) return rc;
-        int end_bit = 32 + ceil_log2((uint32_t)(T > 1 ? T : 2));
-        rc = tgs_sort_instances(bv, I, end_bit, st); if (rc) return rc;
-        if (s->debug) TGS_CUDA(cudaStreamSynchronize(st));
-    }
-    rc = tgs_launch_pack_ranges(gv, bv, I, T, st); if (rc) return rc;
+    rc = tgs_emit_sort_pack(gv, bv, N, I, T, cam.Tx, st); if (rc) return rc;
     if (s->debug) TGS_CUDA(cudaStreamSynchronize(st));
     if ((touch_target == nullptr) != (residual_out == nullptr)) { tgs_set_error("touch_target and residual_out go together"); return TGS_EINVAL; }
     rc = tgs_launch_render_fwd(cam, s, bv, iv, out_color, out_depth, out_alpha, touch_target, residual_out, st); if (rc) return rc;

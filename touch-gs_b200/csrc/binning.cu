@@ -1,111 +1,176 @@
-// binning.cu -- tile binning of the visible Gaussians:
-//   inclusive scan of tiles_touched  ->  duplicateWithKeys  ->  stable 64-bit radix sort
-//   ->  (fused) tile-range detection + packing of the sorted per-instance records.
+// binning.cu -- tile binning of the visible Gaussians.
 //
-// Integer work, bit-exact against oracle/gs_oracle.py::bin_and_sort.  The scan and the sort are
-// CUB device primitives (library code, like calling cuBLAS for a plain GEMM); the kernels around
-// them are ours.  Roofline: HBM.  Algorithmic bytes per instance: key/val write 12,
-// sort 24 (one idealised pass), range detect 8, packed-record gather 48 + write 48.
+// The spec'd RESULT is the list of (tile, Gaussian) instances sorted by the 64-bit key
+// (tile << 32 | bits(depth)), ties in ascending Gaussian id (stable sort of a Gaussian-major emission),
+// plus one [start,end) range per tile.  We produce exactly that list (bit-exact against
+// oracle/gs_oracle.py::bin_and_sort) with a cheaper TWO-PHASE sort:
+//   1. radix-sort the N Gaussians once by depth bits (32-bit keys, N items; stable => equal depths keep
+//      ascending id; invisible Gaussians get key 0xFFFFFFFF and emit nothing);
+//   2. scan tiles_touched in that depth order, emit the instances depth-major (warp-cooperative,
+//      coalesced) with the TILE ID as the only key (16 bits when T <= 65536);
+//   3. stable radix sort of I (tile, id) pairs over ceil(log2 T) bits: 2 onesweep passes on 6-byte pairs
+//      instead of 6 passes on 12-byte pairs.  Stability carries the depth order into every tile.
+//   4. fused tile-range detection + packing of the sorted 48-byte records (gather -> shared memory ->
+//      one TMA bulk store per 256 records, so the packed array is written with full-line stores).
+// The scans / sorts are CUB device primitives (library code, like cuBLAS for a plain GEMM).
+// Roofline: HBM.  Algorithmic bytes per instance: key/val write 12, sort 24, range detect 8,
+// record gather 48 + write 48 (we move 6-byte pairs, so real traffic is below the algorithmic figure).
 #include "tgs_common.cuh"
 #include <cub/cub.cuh>
 
 namespace {
 
-// One warp per Gaussian would waste lanes on the many small splats; one thread per Gaussian
-// serialises the few huge ones.  v1: one thread per Gaussian (A2's definition); emission order is
-// Gaussian-major, then tile row, then tile column -- that order is part of the sort-stability spec.
+constexpr unsigned kFull = 0xffffffffu;
+
+struct TilesInOrder {
+    const uint32_t* tiles; const uint32_t* order;
+    __device__ __forceinline__ uint32_t operator()(uint32_t r) const { return tiles[order[r]]; }
+};
+using TilesIt = cub::TransformInputIterator<uint32_t, TilesInOrder, cub::CountingInputIterator<uint32_t>>;
+
+// Emission in depth order.  One warp per 32 consecutive depth ranks; for each rank with tiles > 0 the
+// whole warp writes that Gaussian's tile list cooperatively (coalesced 2/4-byte stores).
+template <typename KeyT>
 __global__ void __launch_bounds__(256)
-k_duplicate(int N, const TgsRecord* __restrict__ rec, const uint32_t* __restrict__ tiles,
-            const uint32_t* __restrict__ offsets, const uint2* __restrict__ rect, int Tx,
-            uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    if (tiles[i] == 0) return;
-    uint32_t off = (i == 0) ? 0u : offsets[i - 1];
-    uint2 r = rect[i];
-    int x0 = r.x & 0xFFFF, x1 = r.x >> 16, y0 = r.y & 0xFFFF, y1 = r.y >> 16;
-    uint32_t dbits = __float_as_uint(rec[i].a.z);
-    for (int y = y0; y < y1; ++y)
-        for (int x = x0; x < x1; ++x) {
-            uint64_t key = ((uint64_t)(uint32_t)(y * Tx + x) << 32) | dbits;
-            keys[off] = key;
-            vals[off] = (uint32_t)i;
-            ++off;
+k_emit(int N, const uint32_t* __restrict__ order, const uint32_t* __restrict__ tiles,
+       const uint32_t* __restrict__ offsets, const uint2* __restrict__ rect, int Tx,
+       KeyT* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;          // depth rank
+    uint32_t id = 0, cnt = 0, end = 0;
+    uint2 rc = make_uint2(0, 0);
+    if (r < N) {
+        id = order[r];
+        cnt = tiles[id];
+        if (cnt) { end = offsets[r]; rc = rect[id]; }
+    }
+    unsigned mask = __ballot_sync(kFull, cnt != 0);
+    while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const uint32_t gid = __shfl_sync(kFull, id, src);
+        const uint32_t gcnt = __shfl_sync(kFull, cnt, src);
+        const uint32_t gend = __shfl_sync(kFull, end, src);
+        const uint32_t rx = __shfl_sync(kFull, rc.x, src), ry = __shfl_sync(kFull, rc.y, src);
+        const uint32_t x0 = rx & 0xFFFF, w = (rx >> 16) - x0, y0 = ry & 0xFFFF;
+        const uint32_t base = gend - gcnt;
+        for (uint32_t t = lane; t < gcnt; t += 32) {
+            const uint32_t yy = t / w, xx = t - yy * w;              // row-major: y outer, x inner
+            keys[base + t] = (KeyT)((y0 + yy) * Tx + x0 + xx);
+            vals[base + t] = gid;
         }
+    }
 }
 
-// Fused A4 + record packing.  Three threads per instance, one 16-byte quarter of the 48-byte
-// record each, so the packed writes are perfectly coalesced; the thread holding quarter 0 also
-// performs the tile-boundary test of identifyTileRanges.
+// Fused A4 + record packing.  256 instances per CTA: each thread gathers its instance's 48-byte record
+// (3 x LDG.128, mostly L2 hits: the per-Gaussian record array is 48 MB at 1M splats) into shared memory,
+// performs the tile-boundary test of identifyTileRanges, and one thread writes the 12 KB block back with
+// a single TMA bulk store.
+template <typename KeyT>
 __global__ void __launch_bounds__(256)
-k_pack_ranges(int64_t I, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-              const float4* __restrict__ rec_in, float4* __restrict__ rec_out,
-              uint2* __restrict__ ranges) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 3 * I) return;
-    int64_t j = t / 3;
-    int part = (int)(t - 3 * j);
-    uint32_t id = vals[j];
-    rec_out[t] = __ldg(rec_in + (size_t)3 * id + part);
-    if (part == 0) {
-        uint32_t tile = (uint32_t)(keys[j] >> 32);
+k_pack_ranges(int64_t I, const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals,
+              const float4* __restrict__ rec_in, float4* __restrict__ rec_out, uint2* __restrict__ ranges) {
+    __shared__ __align__(128) float4 sm[256 * 3];
+    const int64_t j0 = (int64_t)blockIdx.x * 256;
+    const int64_t j = j0 + threadIdx.x;
+    if (j < I) {
+        const uint32_t id = vals[j];
+        const float4* src = rec_in + (size_t)3 * id;
+        const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+        sm[3 * threadIdx.x] = a; sm[3 * threadIdx.x + 1] = b; sm[3 * threadIdx.x + 2] = c;
+        const uint32_t tile = (uint32_t)keys[j];
         if (j == 0) ranges[tile].x = 0;
         else {
-            uint32_t prev = (uint32_t)(keys[j - 1] >> 32);
+            const uint32_t prev = (uint32_t)keys[j - 1];
             if (prev != tile) { ranges[prev].y = (uint32_t)j; ranges[tile].x = (uint32_t)j; }
         }
         if (j == I - 1) ranges[tile].y = (uint32_t)I;
     }
+    // make the generic-proxy shared-memory writes visible to the async proxy, then bulk-store
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int64_t n = (I - j0) < 256 ? (I - j0) : 256;
+        const uint32_t bytes = (uint32_t)n * 48u;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(rec_out + 3 * j0),
+                     "r"((uint32_t)__cvta_generic_to_shared(sm)), "r"(bytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released after the read
+    }
+}
+
+template <typename KeyT>
+int emit_sort_pack(GeomView gv, BinView bv, int N, int64_t I, int T, int Tx, int tile_bits, cudaStream_t st) {
+    KeyT* ku = reinterpret_cast<KeyT*>(bv.tile_unsorted);
+    KeyT* ks = reinterpret_cast<KeyT*>(bv.tile_sorted);
+    {
+        TgsProfScope prof(TGS_STAGE_DUPLICATE, st);
+        k_emit<KeyT><<<(N + 255) / 256, 256, 0, st>>>(N, gv.order, gv.tiles_touched, gv.offsets, gv.rect, Tx, ku,
+                                                      bv.vals_unsorted);
+        tgs_count_own(1);
+        TGS_CUDA(cudaGetLastError());
+    }
+    {
+        TgsProfScope prof(TGS_STAGE_SORT, st);
+        size_t bytes = bv.cub_temp_bytes;
+        TGS_CUDA(cub::DeviceRadixSort::SortPairs(bv.cub_temp, bytes, ku, ks, bv.vals_unsorted, bv.vals_sorted, I, 0,
+                                                 tile_bits, st));
+        tgs_count_cub(1);
+    }
+    {
+        TgsProfScope prof(TGS_STAGE_PACK, st);
+        k_pack_ranges<KeyT><<<(unsigned)((I + 255) / 256), 256, 0, st>>>(
+            I, ks, bv.vals_sorted, reinterpret_cast<const float4*>(gv.records), reinterpret_cast<float4*>(bv.records),
+            bv.ranges);
+        tgs_count_own(1);
+        TGS_CUDA(cudaGetLastError());
+    }
+    return 0;
 }
 
 }  // namespace
 
-size_t tgs_scan_temp_bytes(int N) {
+size_t tgs_depth_sort_temp_bytes(int N) {
+    size_t a = 0, b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, N, 0, 32);
+    TilesInOrder f{nullptr, nullptr};
+    TilesIt it(cub::CountingInputIterator<uint32_t>(0), f);
+    cub::DeviceScan::InclusiveSum(nullptr, b, it, (uint32_t*)nullptr, N);
+    return a > b ? a : b;
+}
+
+size_t tgs_tile_sort_temp_bytes(int64_t I, int T) {
     size_t bytes = 0;
-    cub::DeviceScan::InclusiveSum(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, N);
+    if (T <= 65536)
+        cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint16_t*)nullptr, (uint16_t*)nullptr,
+                                        (const uint32_t*)nullptr, (uint32_t*)nullptr, I, 0, 16);
+    else
+        cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                        (const uint32_t*)nullptr, (uint32_t*)nullptr, I, 0, 32);
     return bytes;
 }
 
-size_t tgs_sort_temp_bytes(int64_t I, int end_bit) {
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
-                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, I, 0, end_bit);
-    return bytes;
-}
-
-int tgs_scan_tiles(GeomView gv, int N, void* temp, size_t temp_bytes, cudaStream_t st) {
+// Phase 1 + scan: depth order of the Gaussians and the inclusive scan of tiles_touched in that order.
+int tgs_depth_order_and_scan(GeomView gv, int N, cudaStream_t st) {
     TgsProfScope prof(TGS_STAGE_SCAN, st);
-    TGS_CUDA(cub::DeviceScan::InclusiveSum(temp, temp_bytes, gv.tiles_touched, gv.offsets, N, st));
-    tgs_count_cub(1);
+    size_t bytes = gv.temp_bytes;
+    TGS_CUDA(cub::DeviceRadixSort::SortPairs(gv.temp, bytes, gv.depth_keys, gv.depth_keys_sorted, gv.ids, gv.order, N,
+                                             0, 32, st));
+    TilesInOrder f{gv.tiles_touched, gv.order};
+    TilesIt it(cub::CountingInputIterator<uint32_t>(0), f);
+    bytes = gv.temp_bytes;
+    TGS_CUDA(cub::DeviceScan::InclusiveSum(gv.temp, bytes, it, gv.offsets, N, st));
+    tgs_count_cub(2);
     return 0;
 }
 
-int tgs_launch_duplicate(GeomView gv, int N, int Tx, BinView bv, cudaStream_t st) {
-    TgsProfScope prof(TGS_STAGE_DUPLICATE, st);
-    k_duplicate<<<(N + 255) / 256, 256, 0, st>>>(N, gv.records, gv.tiles_touched, gv.offsets, gv.rect, Tx,
-                                                 bv.keys_unsorted, bv.vals_unsorted);
-    tgs_count_own(1);
-    TGS_CUDA(cudaGetLastError());
-    return 0;
-}
-
-int tgs_sort_instances(BinView bv, int64_t I, int end_bit, cudaStream_t st) {
-    TgsProfScope prof(TGS_STAGE_SORT, st);
-    TGS_CUDA(cub::DeviceRadixSort::SortPairs(bv.cub_temp, bv.cub_temp_bytes, bv.keys_unsorted, bv.keys_sorted,
-                                             bv.vals_unsorted, bv.vals_sorted, I, 0, end_bit, st));
-    tgs_count_cub(1);
-    return 0;
-}
-
-int tgs_launch_pack_ranges(GeomView gv, BinView bv, int64_t I, int T, cudaStream_t st) {
-    TgsProfScope prof(TGS_STAGE_PACK, st);
+int tgs_emit_sort_pack(GeomView gv, BinView bv, int N, int64_t I, int T, int Tx, cudaStream_t st) {
     TGS_CUDA(cudaMemsetAsync(bv.ranges, 0, sizeof(uint2) * (size_t)T, st));
     if (I == 0) return 0;
-    int64_t threads = 3 * I;
-    k_pack_ranges<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
-        I, bv.keys_sorted, bv.vals_sorted, reinterpret_cast<const float4*>(gv.records),
-        reinterpret_cast<float4*>(bv.records), bv.ranges);
-    tgs_count_own(1);
-    TGS_CUDA(cudaGetLastError());
-    return 0;
+    int bits = 1;
+    while ((1 << bits) < T) ++bits;
+    if (T <= 65536) return emit_sort_pack<uint16_t>(gv, bv, N, I, T, Tx, bits, st);
+    return emit_sort_pack<uint32_t>(gv, bv, N, I, T, Tx, bits, st);
 }

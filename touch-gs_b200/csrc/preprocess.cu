@@ -30,7 +30,8 @@ k_preprocess(int N, const float* __restrict__ means, const float* __restrict__ s
              const float* __restrict__ pm, const float* __restrict__ campos, TgsCam cam,
              TgsRecord* __restrict__ rec, float* __restrict__ cov3D,
              uint32_t* __restrict__ tiles, uint8_t* __restrict__ clamped,
-             uint2* __restrict__ rect, int32_t* __restrict__ radii) {
+             uint2* __restrict__ rect, uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ ids,
+             int32_t* __restrict__ radii) {
     __shared__ CamMats cm;
     load_cam(vm, pm, campos, &cm);
     int i = blockIdx.x * kBlock + threadIdx.x;
@@ -95,6 +96,8 @@ k_preprocess(int N, const float* __restrict__ means, const float* __restrict__ s
     rect[i] = make_uint2((uint32_t)p.rminx | ((uint32_t)p.rmaxx << 16),
                          (uint32_t)p.rminy | ((uint32_t)p.rmaxy << 16));
     radii[i] = p.radius;
+    depth_keys[i] = p.tiles > 0 ? __float_as_uint(p.depth) : 0xFFFFFFFFu;   // depth > 0.2: bit order == float order
+    ids[i] = (uint32_t)i;
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -192,7 +195,7 @@ int tgs_launch_preprocess(const TgsCam& cam, const TgsSettings* s, const TgsGaus
     k_preprocess<<<(N + kBlock - 1) / kBlock, kBlock, 0, st>>>(
         N, g->means3D, g->scales, g->rotations, g->opacities, g->shs, g->colors_precomp,
         g->cov3D_precomp, s->viewmatrix, s->projmatrix, s->campos, cam, gv.records, gv.cov3D,
-        gv.tiles_touched, gv.clamped, gv.rect, radii);
+        gv.tiles_touched, gv.clamped, gv.rect, gv.depth_keys, gv.ids, radii);
     tgs_count_own(1);
     TGS_KERNEL_CHECK(st, s->debug);
     return 0;

@@ -54,10 +54,15 @@ struct GeomView {
     uint32_t* offsets;       // [N] inclusive scan
     uint8_t* clamped;        // [N] bit c = colour channel c clamped at 0
     uint2* rect;             // [N] (rminx | rmaxx<<16, rminy | rmaxy<<16)
+    uint32_t* depth_keys;    // [N] bits(depth) or 0xFFFFFFFF
+    uint32_t* ids;           // [N] iota
+    uint32_t* depth_keys_sorted;
+    uint32_t* order;         // [N] ids in (depth, id) order
+    void* temp; size_t temp_bytes;
 };
 struct BinView {
-    uint64_t* keys_unsorted; uint32_t* vals_unsorted;
-    uint64_t* keys_sorted;   uint32_t* vals_sorted;
+    void* tile_unsorted; uint32_t* vals_unsorted;   // tile ids are uint16 when T <= 65536, else uint32
+    void* tile_sorted;   uint32_t* vals_sorted;
     uint2* ranges;           // [T]
     TgsRecord* records;      // [I] packed, sorted
     void* cub_temp; size_t cub_temp_bytes;
@@ -68,8 +73,8 @@ struct ImageView {
 GeomView tgs_geom_view(void* base, int N);
 BinView tgs_bin_view(void* base, int64_t I, int T);
 ImageView tgs_image_view(void* base, int W, int H);
-size_t tgs_sort_temp_bytes(int64_t I, int end_bit);
-size_t tgs_scan_temp_bytes(int N);
+size_t tgs_tile_sort_temp_bytes(int64_t I, int T);
+size_t tgs_depth_sort_temp_bytes(int N);
 
 // ------------------------------------------------------------------------ kernel launchers
 // preprocess.cu
@@ -80,10 +85,8 @@ int tgs_launch_preprocess_bwd(const TgsCam& cam, const TgsSettings* s, const Tgs
                               const TgsGrads* grads, cudaStream_t st);
 int tgs_launch_mark_visible(int N, const float* means, const float* vm, uint8_t* present, cudaStream_t st);
 // binning.cu
-int tgs_scan_tiles(GeomView gv, int N, void* temp, size_t temp_bytes, cudaStream_t st);
-int tgs_launch_duplicate(GeomView gv, int N, int Tx, BinView bv, cudaStream_t st);
-int tgs_sort_instances(BinView bv, int64_t I, int end_bit, cudaStream_t st);
-int tgs_launch_pack_ranges(GeomView gv, BinView bv, int64_t I, int T, cudaStream_t st);
+int tgs_depth_order_and_scan(GeomView gv, int N, cudaStream_t st);
+int tgs_emit_sort_pack(GeomView gv, BinView bv, int N, int64_t I, int T, int Tx, cudaStream_t st);
 // render.cu
 int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, BinView bv, ImageView iv,
                           float* out_color, float* out_depth, float* out_alpha,

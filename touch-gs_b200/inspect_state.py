@@ -20,6 +20,12 @@ def _view(buf: torch.Tensor, off: int, count: int, dtype: torch.dtype) -> torch.
     return buf[off:off + nbytes].view(dtype)
 
 
+def _tiles(buf, off, count, key_bytes):
+    if key_bytes == 2:
+        return (_view(buf, off, count, torch.int16).to(torch.int64)) & 0xFFFF
+    return (_view(buf, off, count, torch.int32).to(torch.int64)) & 0xFFFFFFFF
+
+
 def forward_state(means3D, opacities, rs: GaussianRasterizationSettings, shs=None, colors_precomp=None,
                   scales=None, rotations=None, cov3D_precomp=None, opt: TouchOptions = None) -> Dict[str, torch.Tensor]:
     """Run the operator's forward (no grad) and return outputs + decoded internal state."""
@@ -59,9 +65,10 @@ def forward_state(means3D, opacities, rs: GaussianRasterizationSettings, shs=Non
         clamped=_view(geom, gl.clamped, N, torch.uint8),
         rect_min=torch.stack([rect[:, 0] & 0xFFFF, rect[:, 1] & 0xFFFF], -1),
         rect_max=torch.stack([(rect[:, 0] >> 16) & 0xFFFF, (rect[:, 1] >> 16) & 0xFFFF], -1),
-        keys_unsorted=_view(binning, bl.keys_unsorted, I, torch.int64),
-        vals_unsorted=_view(binning, bl.vals_unsorted, I, torch.int32),
-        keys=_view(binning, bl.keys_sorted, I, torch.int64),
+        order=_view(geom, gl.order, N, torch.int32),
+        tile_ids=_tiles(binning, bl.tile_sorted, I, bl.key_bytes),
+        tile_ids_emitted=_tiles(binning, bl.tile_unsorted, I, bl.key_bytes),
+        vals_emitted=_view(binning, bl.vals_unsorted, I, torch.int32),
         vals=_view(binning, bl.vals_sorted, I, torch.int32),
         ranges=_view(binning, bl.ranges, Tx * Ty * 2, torch.int32).view(Tx * Ty, 2),
         records=_view(binning, bl.records, I * 12, torch.float32).view(I, 12),
@@ -69,4 +76,7 @@ def forward_state(means3D, opacities, rs: GaussianRasterizationSettings, shs=Non
         n_contrib=_view(image, il.n_contrib, H * W, torch.int32).view(H, W),
         depth_raw=_view(image, il.depth_raw, H * W, torch.float32).view(H, W),
     )
+    # the spec'd 64-bit sort key of every sorted instance: tile << 32 | bits(depth of its Gaussian)
+    dbits = out["gdepth"].contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    out["keys"] = (out["tile_ids"] << 32) | dbits[out["vals"].long()]
     return out

@@ -75,22 +75,29 @@ def _chk(t: Optional[torch.Tensor], name: str, shape, device, dtype=torch.float3
 
 class _Scratch:
     """Allocator handed to the C ABI: the three saved byte buffers are torch tensors, so they come
-    from torch's caching allocator on the caller's device and are kept alive by ``ctx``."""
+    from torch's caching allocator on the caller's device and are kept alive by ``ctx``.
+
+    The ctypes callback closes over a plain dict, never over ``self``: a bound-method callback would
+    form a reference cycle that keeps ~1 GB of scratch per call alive until the cyclic GC runs."""
 
     def __init__(self, device):
-        self.device = device
-        self.bufs = {}
-        self.error = None
-        self.cb = L.ALLOC_FN(self._alloc)
+        bufs, err = {}, []
 
-    def _alloc(self, _user, which, nbytes):
-        try:
-            t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
-            self.bufs[int(which)] = t
-            return t.data_ptr()
-        except Exception as e:  # noqa: BLE001 - must not propagate through the C frame
-            self.error = e
-            return None
+        def _alloc(_user, which, nbytes, _device=device, _bufs=bufs, _err=err):
+            try:
+                t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=_device)
+                _bufs[int(which)] = t
+                return t.data_ptr()
+            except Exception as e:  # noqa: BLE001 - must not propagate through the C frame
+                _err.append(e)
+                return None
+
+        self.bufs, self._err = bufs, err
+        self.cb = L.ALLOC_FN(_alloc)
+
+    @property
+    def error(self):
+        return self._err[0] if self._err else None
 
 
 def _stream_ptr(device):
