@@ -50,15 +50,10 @@ void hm_backward(int N, const float* means, const float* scales, const float* ro
             else tgs_cov3d(scales + 3 * i, cam->mod, rots + 4 * i, cov);
             tgs_project_backward(vm, pm, *cam, means[3 * i], means[3 * i + 1], means[3 * i + 2], cov,
                                  sg + 10 * i, dm, dc);
-            if (shs) {
-                float sh48[48], dsh48[48];
-                int nb = (cam->deg + 1) * (cam->deg + 1);
-                for (int k = 0; k < 48; ++k) sh48[k] = (k < 3 * nb) ? shs[3 * cam->K * i + k] : 0.0f;
-                tgs_sh_backward(cam->deg, cam->K, sh48, means[3 * i] - campos[0],
+            if (shs)
+                tgs_sh_backward(cam->deg, cam->K, shs + 3 * cam->K * i, means[3 * i] - campos[0],
                                 means[3 * i + 1] - campos[1], means[3 * i + 2] - campos[2],
-                                sg + 10 * i + 6, clamped[i], dsh48, dm);
-                for (int k = 0; k < 3 * cam->K; ++k) dsh[3 * cam->K * i + k] = dsh48[k];
-            }
+                                sg + 10 * i + 6, clamped[i], dsh + 3 * cam->K * i, dm);
             if (!cov_pre) tgs_cov3d_backward(scales + 3 * i, cam->mod, rots + 4 * i, dc, ds, dq);
         } else if (shs) {
             for (int k = 0; k < 3 * cam->K; ++k) dsh[3 * cam->K * i + k] = 0.0f;

@@ -130,24 +130,9 @@ k_preprocess_bwd(int N, const float* __restrict__ means, const float* __restrict
         for (int k = 0; k < 6; ++k) cov[k] = cov3D[6 * i + k];
         tgs_project_backward(cm.vm, cm.pm, cam, x, y, z, cov, sg, dm, dc);
         if (shs) {
-            float sh[48], dsh[48];
-            const float* src = shs + (size_t)3 * cam.K * i;
-            int nb = (cam.deg + 1) * (cam.deg + 1);
-#pragma unroll
-            for (int k = 0; k < 48; ++k) sh[k] = (k < 3 * nb) ? __ldg(src + k) : 0.0f;
-            tgs_sh_backward(cam.deg, cam.K, sh, x - cm.cp[0], y - cm.cp[1], z - cm.cp[2],
-                            sg + 6, clamped[i], dsh, dm);
-            float* dst = dshs + (size_t)3 * cam.K * i;
-            if (((3 * cam.K) & 3) == 0) {
-                float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll
-                for (int k = 0; k < 12; ++k)
-                    if (4 * k < 3 * cam.K) d4[k] = make_float4(dsh[4 * k], dsh[4 * k + 1], dsh[4 * k + 2], dsh[4 * k + 3]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 48; ++k)
-                    if (k < 3 * cam.K) dst[k] = dsh[k];
-            }
+            // streams the K coefficients in groups of 4 straight from / to global memory
+            tgs_sh_backward(cam.deg, cam.K, shs + (size_t)3 * cam.K * i, x - cm.cp[0], y - cm.cp[1], z - cm.cp[2],
+                            sg + 6, clamped[i], dshs + (size_t)3 * cam.K * i, dm);
         }
         if (!covpre) {
             float4 q = reinterpret_cast<const float4*>(rots)[i];

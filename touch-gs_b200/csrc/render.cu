@@ -355,33 +355,34 @@ k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
                 const float alpha = splat_alpha(cq.w, G);
                 const bool valid = (idx < nc) && (power <= 0.0f) && (alpha >= TGS_ALPHA_MIN);
                 if (!__any_sync(kFull, valid)) continue;
-                float v[TGS_NGRAD];
-#pragma unroll
-                for (int k = 0; k < TGS_NGRAD; ++k) v[k] = 0.0f;
-                if (valid) {
-                    const float4 c = s[3 * j + 2];
-                    const float inv = 1.0f / (1.0f - alpha);
-                    T = T * inv;                               // transmittance in front of this splat
-                    const float w = alpha * T;
-                    const float om = 1.0f - last_alpha;
-                    ac0 = last_alpha * lc0 + om * ac0; lc0 = c.x;
-                    ac1 = last_alpha * lc1 + om * ac1; lc1 = c.y;
-                    ac2 = last_alpha * lc2 + om * ac2; lc2 = c.z;
-                    acD = last_alpha * lcD + om * acD; lcD = a.z;
-                    float dLda = (c.x - ac0) * g0 + (c.y - ac1) * g1 + (c.z - ac2) * g2 + (a.z - acD) * gD;
-                    dLda = dLda * T + tail * inv;
+                // Branch-free body: lanes that do not blend this splat run with alpha masked to 0, which
+                // makes every gradient value exactly 0 and leaves T untouched (inv == 1); only the small
+                // state update below is predicated.
+                const float4 c = s[3 * j + 2];
+                const float am = valid ? alpha : 0.0f;
+                const float inv = __fdividef(1.0f, 1.0f - am);
+                T = T * inv;                                   // transmittance in front of this splat
+                const float w = am * T;
+                if (valid) {                                   // colour / depth accumulated BEHIND this splat
+                    ac0 = fmaf(last_alpha, lc0 - ac0, ac0); lc0 = c.x;
+                    ac1 = fmaf(last_alpha, lc1 - ac1, ac1); lc1 = c.y;
+                    ac2 = fmaf(last_alpha, lc2 - ac2, ac2); lc2 = c.z;
+                    acD = fmaf(last_alpha, lcD - acD, acD); lcD = a.z;
                     last_alpha = alpha;
-                    const float dLdG = cq.w * dLda;
-                    const float gdx = G * dx, gdy = G * dy;
-                    v[0] = dLdG * (-gdx * cq.x - gdy * cq.y);
-                    v[1] = dLdG * (-gdy * cq.z - gdx * cq.y);
-                    v[2] = -0.5f * gdx * dx * dLdG;
-                    v[3] = -gdx * dy * dLdG;
-                    v[4] = -0.5f * gdy * dy * dLdG;
-                    v[5] = G * dLda;
-                    v[6] = w * g0; v[7] = w * g1; v[8] = w * g2;
-                    v[9] = w * gD;
                 }
+                float dLda = (c.x - ac0) * g0 + (c.y - ac1) * g1 + (c.z - ac2) * g2 + (a.z - acD) * gD;
+                dLda = valid ? fmaf(dLda, T, tail * inv) : 0.0f;
+                const float dLdG = cq.w * dLda;
+                const float gdx = G * dx, gdy = G * dy;
+                float v[TGS_NGRAD];
+                v[0] = dLdG * (-gdx * cq.x - gdy * cq.y);
+                v[1] = dLdG * (-gdy * cq.z - gdx * cq.y);
+                v[2] = -0.5f * gdx * dx * dLdG;
+                v[3] = -gdx * dy * dLdG;
+                v[4] = -0.5f * gdy * dy * dLdG;
+                v[5] = G * dLda;
+                v[6] = w * g0; v[7] = w * g1; v[8] = w * g2;
+                v[9] = w * gD;
                 float sum; int slot; bool ok;
                 warp_reduce_scatter10(v, lane, sum, slot, ok);
                 if (ok) atomicAdd(sgrad + (size_t)__float_as_int(a.w) * TGS_NGRAD + slot, sum);

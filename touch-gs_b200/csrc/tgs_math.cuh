@@ -209,72 +209,116 @@ TGS_HD void tgs_sh_forward(int deg, const float* sh, float dx, float dy, float d
     }
 }
 
+// Basis function k of the real SH expansion at unit direction (x,y,z) and its gradient.
+// `k` is a compile-time constant at every call site (fully unrolled loops), so the switch folds.
+TGS_HD void tgs_sh_basis(int k, float x, float y, float z, float& b, float& bx, float& by, float& bz) {
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    b = bx = by = bz = 0.0f;
+    switch (k) {
+        case 0: b = TGS_SH_C0; break;
+        case 1: b = -TGS_SH_C1 * y; by = -TGS_SH_C1; break;
+        case 2: b = TGS_SH_C1 * z; bz = TGS_SH_C1; break;
+        case 3: b = -TGS_SH_C1 * x; bx = -TGS_SH_C1; break;
+        case 4: b = TGS_SH_C2_0 * xy; bx = TGS_SH_C2_0 * y; by = TGS_SH_C2_0 * x; break;
+        case 5: b = TGS_SH_C2_1 * yz; by = TGS_SH_C2_1 * z; bz = TGS_SH_C2_1 * y; break;
+        case 6: b = TGS_SH_C2_2 * (2.0f * zz - xx - yy);
+                bx = TGS_SH_C2_2 * -2.0f * x; by = TGS_SH_C2_2 * -2.0f * y; bz = TGS_SH_C2_2 * 4.0f * z; break;
+        case 7: b = TGS_SH_C2_3 * xz; bx = TGS_SH_C2_3 * z; bz = TGS_SH_C2_3 * x; break;
+        case 8: b = TGS_SH_C2_4 * (xx - yy); bx = TGS_SH_C2_4 * 2.0f * x; by = TGS_SH_C2_4 * -2.0f * y; break;
+        case 9: b = TGS_SH_C3_0 * y * (3.0f * xx - yy);
+                bx = TGS_SH_C3_0 * 6.0f * xy; by = TGS_SH_C3_0 * (3.0f * xx - 3.0f * yy); break;
+        case 10: b = TGS_SH_C3_1 * xy * z; bx = TGS_SH_C3_1 * yz; by = TGS_SH_C3_1 * xz; bz = TGS_SH_C3_1 * xy; break;
+        case 11: b = TGS_SH_C3_2 * y * (4.0f * zz - xx - yy);
+                 bx = TGS_SH_C3_2 * -2.0f * xy; by = TGS_SH_C3_2 * (4.0f * zz - xx - 3.0f * yy);
+                 bz = TGS_SH_C3_2 * 8.0f * yz; break;
+        case 12: b = TGS_SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+                 bx = TGS_SH_C3_3 * -6.0f * xz; by = TGS_SH_C3_3 * -6.0f * yz;
+                 bz = TGS_SH_C3_3 * (6.0f * zz - 3.0f * xx - 3.0f * yy); break;
+        case 13: b = TGS_SH_C3_4 * x * (4.0f * zz - xx - yy);
+                 bx = TGS_SH_C3_4 * (4.0f * zz - 3.0f * xx - yy); by = TGS_SH_C3_4 * -2.0f * xy;
+                 bz = TGS_SH_C3_4 * 8.0f * xz; break;
+        case 14: b = TGS_SH_C3_5 * z * (xx - yy);
+                 bx = TGS_SH_C3_5 * 2.0f * xz; by = TGS_SH_C3_5 * -2.0f * yz; bz = TGS_SH_C3_5 * (xx - yy); break;
+        case 15: b = TGS_SH_C3_6 * x * (xx - 3.0f * yy);
+                 bx = TGS_SH_C3_6 * (3.0f * xx - 3.0f * yy); by = TGS_SH_C3_6 * -6.0f * xy; break;
+        default: break;
+    }
+}
+
+// Backward of 4 consecutive coefficients (k = 4*grp .. 4*grp+3): sh12 / dsh12 hold [4][3] floats.
+// nb = number of ACTIVE coefficients; inactive ones get zero gradient and add nothing to ddir.
+// Streaming the 16 coefficients in 4 groups keeps the register footprint small (12 + 12 live floats).
+TGS_HD void tgs_sh_backward_group(int grp, int nb, float x, float y, float z, const float* sh12,
+                                  const float* g, float* dsh12, float& ddx, float& ddy, float& ddz) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 4; ++i) {
+        const int k = 4 * grp + i;
+        float b, bx, by, bz;
+        tgs_sh_basis(k, x, y, z, b, bx, by, bz);
+        const bool act = k < nb;
+        const float s = act ? (sh12[3 * i] * g[0] + sh12[3 * i + 1] * g[1] + sh12[3 * i + 2] * g[2]) : 0.0f;
+        ddx += bx * s; ddy += by * s; ddz += bz * s;
+        dsh12[3 * i] = act ? b * g[0] : 0.0f;
+        dsh12[3 * i + 1] = act ? b * g[1] : 0.0f;
+        dsh12[3 * i + 2] = act ? b * g[2] : 0.0f;
+    }
+}
+
 // dL/dsh [K][3] (fully written: zero above the active degree) and dL/d(mean) through the view
-// direction.  drgb is zeroed where the forward clamped.
+// direction.  drgb is zeroed where the forward clamped.  `sh` / `dsh` may be global pointers: they are
+// read / written in groups of 4 coefficients.
 TGS_HD void tgs_sh_backward(int deg, int K, const float* sh, float dx, float dy, float dz,
                             const float* drgb_in, unsigned clamped, float* dsh, float* dmean) {
     float g[3];
     for (int c = 0; c < 3; ++c) g[c] = ((clamped >> c) & 1u) ? 0.0f : drgb_in[c];
-    float ln = sqrtf((dx * dx + dy * dy) + dz * dz);
-    float inv = 1.0f / ln;
-    float x = dx * inv, y = dy * inv, z = dz * inv;
-    float b[16], bx[16], by[16], bz[16];
+    const float ln = sqrtf((dx * dx + dy * dy) + dz * dz);
+    const float inv = 1.0f / ln;
+    const float x = dx * inv, y = dy * inv, z = dz * inv;
+    const int nb = (deg + 1) * (deg + 1);
+    float ddx = 0.0f, ddy = 0.0f, ddz = 0.0f;
+    const bool vec = ((3 * K) & 3) == 0;           // K*12 bytes is a multiple of 16: float4 path
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int k = 0; k < 16; ++k) { b[k] = bx[k] = by[k] = bz[k] = 0.0f; }
-    b[0] = TGS_SH_C0;
-    int nb = 1;
-    if (deg > 0) {
-        b[1] = -TGS_SH_C1 * y; by[1] = -TGS_SH_C1;
-        b[2] = TGS_SH_C1 * z;  bz[2] = TGS_SH_C1;
-        b[3] = -TGS_SH_C1 * x; bx[3] = -TGS_SH_C1;
-        nb = 4;
-        if (deg > 1) {
-            float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-            b[4] = TGS_SH_C2_0 * xy; bx[4] = TGS_SH_C2_0 * y; by[4] = TGS_SH_C2_0 * x;
-            b[5] = TGS_SH_C2_1 * yz; by[5] = TGS_SH_C2_1 * z; bz[5] = TGS_SH_C2_1 * y;
-            b[6] = TGS_SH_C2_2 * (2.0f * zz - xx - yy);
-            bx[6] = TGS_SH_C2_2 * -2.0f * x; by[6] = TGS_SH_C2_2 * -2.0f * y; bz[6] = TGS_SH_C2_2 * 4.0f * z;
-            b[7] = TGS_SH_C2_3 * xz; bx[7] = TGS_SH_C2_3 * z; bz[7] = TGS_SH_C2_3 * x;
-            b[8] = TGS_SH_C2_4 * (xx - yy); bx[8] = TGS_SH_C2_4 * 2.0f * x; by[8] = TGS_SH_C2_4 * -2.0f * y;
-            nb = 9;
-            if (deg > 2) {
-                b[9] = TGS_SH_C3_0 * y * (3.0f * xx - yy);
-                bx[9] = TGS_SH_C3_0 * 6.0f * xy; by[9] = TGS_SH_C3_0 * (3.0f * xx - 3.0f * yy);
-                b[10] = TGS_SH_C3_1 * xy * z;
-                bx[10] = TGS_SH_C3_1 * yz; by[10] = TGS_SH_C3_1 * xz; bz[10] = TGS_SH_C3_1 * xy;
-                b[11] = TGS_SH_C3_2 * y * (4.0f * zz - xx - yy);
-                bx[11] = TGS_SH_C3_2 * -2.0f * xy; by[11] = TGS_SH_C3_2 * (4.0f * zz - xx - 3.0f * yy);
-                bz[11] = TGS_SH_C3_2 * 8.0f * yz;
-                b[12] = TGS_SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
-                bx[12] = TGS_SH_C3_3 * -6.0f * xz; by[12] = TGS_SH_C3_3 * -6.0f * yz;
-                bz[12] = TGS_SH_C3_3 * (6.0f * zz - 3.0f * xx - 3.0f * yy);
-                b[13] = TGS_SH_C3_4 * x * (4.0f * zz - xx - yy);
-                bx[13] = TGS_SH_C3_4 * (4.0f * zz - 3.0f * xx - yy); by[13] = TGS_SH_C3_4 * -2.0f * xy;
-                bz[13] = TGS_SH_C3_4 * 8.0f * xz;
-                b[14] = TGS_SH_C3_5 * z * (xx - yy);
-                bx[14] = TGS_SH_C3_5 * 2.0f * xz; by[14] = TGS_SH_C3_5 * -2.0f * yz; bz[14] = TGS_SH_C3_5 * (xx - yy);
-                b[15] = TGS_SH_C3_6 * x * (xx - 3.0f * yy);
-                bx[15] = TGS_SH_C3_6 * (3.0f * xx - 3.0f * yy); by[15] = TGS_SH_C3_6 * -6.0f * xy;
-                nb = 16;
+    for (int grp = 0; grp < 4; ++grp) {
+        if (4 * grp >= K) break;
+        float s12[12], d12[12];
+        if (vec) {
+#if defined(__CUDA_ARCH__)
+            if (4 * grp < nb) {
+                const float4* p = reinterpret_cast<const float4*>(sh + 12 * grp);
+                const float4 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2);
+                s12[0] = v0.x; s12[1] = v0.y; s12[2] = v0.z; s12[3] = v0.w; s12[4] = v1.x; s12[5] = v1.y;
+                s12[6] = v1.z; s12[7] = v1.w; s12[8] = v2.x; s12[9] = v2.y; s12[10] = v2.z; s12[11] = v2.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 12; ++i) s12[i] = 0.0f;
             }
+#else
+            for (int i = 0; i < 12; ++i) s12[i] = (4 * grp < nb) ? sh[12 * grp + i] : 0.0f;
+#endif
+        } else {
+            for (int i = 0; i < 12; ++i) s12[i] = (12 * grp + i < 3 * K && 4 * grp + i / 3 < nb) ? sh[12 * grp + i] : 0.0f;
+        }
+        tgs_sh_backward_group(grp, nb, x, y, z, s12, g, d12, ddx, ddy, ddz);
+        if (vec) {
+#if defined(__CUDA_ARCH__)
+            float4* q = reinterpret_cast<float4*>(dsh + 12 * grp);
+            q[0] = make_float4(d12[0], d12[1], d12[2], d12[3]);
+            q[1] = make_float4(d12[4], d12[5], d12[6], d12[7]);
+            q[2] = make_float4(d12[8], d12[9], d12[10], d12[11]);
+#else
+            for (int i = 0; i < 12; ++i) dsh[12 * grp + i] = d12[i];
+#endif
+        } else {
+            for (int i = 0; i < 12; ++i)
+                if (12 * grp + i < 3 * K) dsh[12 * grp + i] = d12[i];
         }
     }
-    // `sh` holds 48 floats (zeros above the active degree); `dsh` receives 48 floats (zeros above it);
-    // the caller stores the first 3*K of them.  Full-length loops keep device code in registers.
-    (void)K; (void)nb;
-    float ddx = 0.0f, ddy = 0.0f, ddz = 0.0f;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int k = 0; k < 16; ++k) {
-        float s = sh[3 * k] * g[0] + sh[3 * k + 1] * g[1] + sh[3 * k + 2] * g[2];
-        ddx += bx[k] * s; ddy += by[k] * s; ddz += bz[k] * s;
-        dsh[3 * k] = b[k] * g[0]; dsh[3 * k + 1] = b[k] * g[1]; dsh[3 * k + 2] = b[k] * g[2];
-    }
     // d = raw/|raw| :  dL/draw = (dd - d (d.dd)) / |raw|
-    float dot = x * ddx + y * ddy + z * ddz;
+    const float dot = x * ddx + y * ddy + z * ddz;
     dmean[0] += (ddx - x * dot) * inv;
     dmean[1] += (ddy - y * dot) * inv;
     dmean[2] += (ddz - z * dot) * inv;
