@@ -79,6 +79,19 @@ __device__ __forceinline__ float splat_power(const float4 q, float dx, float dy)
 __device__ __forceinline__ float splat_alpha(float opacity, float G) {
     return fminf(TGS_ALPHA_MAX, __fmul_rn(opacity, G));
 }
+// exp(power) = ex2(power*log2e) with flush-to-zero: one FMUL + one MUFU.EX2, no denormal fix-up code.
+// (power <= 0 here; results below 2^-126 flush to 0, far under the 1/255 alpha threshold.)
+__device__ __forceinline__ float splat_exp(float power) {
+    float y;
+    const float x = __fmul_rn(power, 1.4426950408889634f);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 struct PixelMap {
     int px, py, pix; bool inside; float fx, fy;
@@ -180,7 +193,7 @@ k_render_fwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
                 const float4 a = s[3 * j], q = s[3 * j + 1];
                 const float dx = a.x - pm.fx, dy = a.y - pm.fy;
                 const float power = splat_power(q, dx, dy);
-                const float alpha = splat_alpha(q.w, __expf(power));
+                const float alpha = splat_alpha(q.w, splat_exp(power));
                 bool valid = !done && (power <= 0.0f) && (alpha >= TGS_ALPHA_MIN);
                 if (!__any_sync(kFull, valid)) continue;
                 const float test_T = T * (1.0f - alpha);
@@ -249,7 +262,7 @@ __device__ __forceinline__ void warp_reduce_scatter10(const float (&v)[TGS_NGRAD
     valid = !(lane & 1) && ((lane & 8) ? !(lane & 4) : !((lane & 4) && (lane & 2)));
 }
 
-// Backward: ONE WARP PER 16x8 HALF TILE, FOUR PIXELS PER THREAD (a vertical strip x, y0..y0+3).
+// Backward: ONE SINGLE-WARP CTA PER 16x8 HALF TILE, FOUR PIXELS PER THREAD (a vertical strip x, y0..y0+3).
 // Measured at c3 (1M splats, 1080p): 5.16 M contributing (8x4 patch, splat) pairs but only 1.84 M
 // contributing (16x8 patch, splat) pairs, so the warp reduction + REDs -- a third of the work of the
 // one-pixel-per-thread kernel -- are paid 2.8x less often.  dx is shared by a thread's four pixels, so
@@ -257,8 +270,8 @@ __device__ __forceinline__ void warp_reduce_scatter10(const float (&v)[TGS_NGRAD
 //   U0 = sum u,  U1 = sum u*dy,  U2 = sum u*dy^2     with u = o*G*dL/dalpha
 // from which  d/dx = -(A dx U0 + B U1), d/dy = -(C U1 + B dx U0), dA = -dx^2 U0/2, dB = -dx U1,
 // dC = -U2/2, do = U0/o.   "Colour behind" is tracked as R <- R + alpha (c - R) (no delayed update).
-constexpr int kBwdThreads = 64;
-constexpr int kBwdBatch = 128;
+constexpr int kBwdThreads = 32;                 // ONE independent warp per CTA: no block barriers at all
+constexpr int kBwdBatch = 64;
 constexpr int kPix = 4;
 
 __global__ void __launch_bounds__(kBwdThreads)
@@ -271,17 +284,17 @@ k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
              float* __restrict__ residual, float* __restrict__ sgrad) {
     __shared__ __align__(128) float4 sbuf[2][kBwdBatch * 3];
     __shared__ __align__(8) uint64_t full[2];
-    __shared__ uint32_t s_max[2];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x + row0 * Tx;
+    const int lane = threadIdx.x;
+    const int half = blockIdx.x & 1;                 // upper / lower 16x8 half of the tile
+    const int tile = (blockIdx.x >> 1) + row0 * Tx;
     const uint2 rng = ranges[tile];
     const int len = (int)(rng.y - rng.x);
     const int tx = tile % Tx, ty = tile / Tx;
     const int px = tx * TGS_TILE + (lane & 15);
-    const int py0 = ty * TGS_TILE + warp * 8 + (lane >> 4) * kPix;
+    const int py0 = ty * TGS_TILE + half * 8 + (lane >> 4) * kPix;
     PixelMap pm;                                   // only the cull rectangle of this warp is used
     pm.x0 = (float)(tx * TGS_TILE); pm.x1 = pm.x0 + 15.0f;
-    pm.y0 = (float)(ty * TGS_TILE + warp * 8); pm.y1 = pm.y0 + 7.0f;
+    pm.y0 = (float)(ty * TGS_TILE + half * 8); pm.y1 = pm.y0 + 7.0f;
     const float fx = (float)px, fy0 = (float)py0;
 
     // ---- per-pixel state and the FUSED touch-depth gradient (SURVEY A6 "Fusion")
@@ -329,15 +342,14 @@ k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
             wmax = max(wmax, nc[r]);
         }
     }
-    // ---- nothing beyond the deepest contributor of any pixel needs replaying (tile- and warp-level)
+    // ---- nothing beyond the deepest contributor of any pixel of this half tile needs replaying
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(kFull, wmax, o));
-    if (lane == 0) s_max[warp] = wmax;
-    if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
-    __syncthreads();
-    const int leff = min(len, (int)max(s_max[0], s_max[1]));
+    const int leff = min(len, (int)wmax);
     const int nb = (leff + kBwdBatch - 1) / kBwdBatch;
     if (nb == 0) return;
+    if (lane == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
+    __syncwarp();
 
     const TgsRecord* src = recs + rng.x;
     auto issue = [&](int q) {                       // sequence step q stages batch nb-1-q (back to front)
@@ -347,7 +359,7 @@ k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
         mbar_expect_tx(&full[q & 1], bytes);
         tma_bulk_g2s(sbuf[q & 1], src + (size_t)b * kBwdBatch, bytes, &full[q & 1]);
     };
-    if (tid == 0) { issue(0); if (nb > 1) issue(1); }
+    if (lane == 0) { issue(0); if (nb > 1) issue(1); }
 
     float R0[kPix], R1[kPix], R2[kPix], RD[kPix];   // colour / depth composited BEHIND the current splat
 #pragma unroll
@@ -360,11 +372,9 @@ k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
         const float4* s = sbuf[q & 1];
         const int base = b * kBwdBatch;
         for (int c0 = ((cnt - 1) >> 5) << 5; c0 >= 0; c0 -= 32) {
-            if ((uint32_t)(base + c0) >= wmax) continue;        // beyond this warp's deepest contributor
             const int jl = c0 + lane;
             bool pass = false;
-            if (jl < cnt && (uint32_t)(base + jl) < wmax)
-                pass = patch_may_touch(s[3 * jl], s[3 * jl + 1], s[3 * jl + 2].w, pm);
+            if (jl < cnt) pass = patch_may_touch(s[3 * jl], s[3 * jl + 1], s[3 * jl + 2].w, pm);
             unsigned mask = __ballot_sync(kFull, pass);
             while (mask) {
                 const int hb = 31 - __clz(mask);
@@ -376,36 +386,35 @@ k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
                 const float dx = a.x - fx;
                 const float t1 = __fmul_rn(__fmul_rn(cq.x, dx), dx);
                 const float bxd = __fmul_rn(cq.y, dx);
-                float G[kPix], al[kPix], dy[kPix];
-                bool valid[kPix];
+                float og[kPix], dy[kPix];             // og = o*G where the pixel blends this splat, else 0
                 bool anyv = false;
 #pragma unroll
                 for (int r = 0; r < kPix; ++r) {
                     dy[r] = a.y - (fy0 + (float)r);
                     const float sq = __fmaf_rn(__fmul_rn(cq.z, dy[r]), dy[r], t1);
                     const float power = __fmaf_rn(-0.5f, sq, -__fmul_rn(bxd, dy[r]));
-                    G[r] = __expf(power);
-                    al[r] = splat_alpha(cq.w, G[r]);
-                    valid[r] = (idx < nc[r]) && (power <= 0.0f) && (al[r] >= TGS_ALPHA_MIN);
-                    anyv |= valid[r];
+                    const float oG = __fmul_rn(cq.w, splat_exp(power));
+                    const bool valid = (idx < nc[r]) && (power <= 0.0f) && (oG >= TGS_ALPHA_MIN);   // min(0.99,oG) >= 1/255 <=> oG >= 1/255
+                    og[r] = valid ? oG : 0.0f;
+                    anyv |= valid;
                 }
                 if (!__any_sync(kFull, anyv)) continue;
                 const float4 c = s[3 * j + 2];
                 float U0 = 0.f, U1 = 0.f, U2 = 0.f, V0 = 0.f, V1 = 0.f, V2 = 0.f, VD = 0.f;
 #pragma unroll
                 for (int r = 0; r < kPix; ++r) {
-                    // lanes/pixels that do not blend this splat run with alpha masked to 0: every gradient
-                    // term becomes exactly 0 and T is untouched (inv == 1)
-                    const float am = valid[r] ? al[r] : 0.0f;
-                    const float inv = __fdividef(1.0f, 1.0f - am);
+                    // pixels that do not blend this splat run with og == 0: alpha == 0, inv == 1, T untouched,
+                    // u == 0 and w == 0, so every gradient term is exactly 0 without any branch
+                    const float am = fminf(TGS_ALPHA_MAX, og[r]);
+                    const float inv = fast_rcp(1.0f - am);
                     T[r] *= inv;                               // transmittance in front of this splat
                     const float w = am * T[r];
                     const float d0 = c.x - R0[r], d1 = c.y - R1[r], d2 = c.z - R2[r], dD = a.z - RD[r];
                     float dLda = d0 * g0[r] + d1 * g1[r] + d2 * g2[r] + dD * gD[r];
-                    dLda = valid[r] ? fmaf(dLda, T[r], tail[r] * inv) : 0.0f;
+                    dLda = fmaf(dLda, T[r], tail[r] * inv);
                     R0[r] = fmaf(am, d0, R0[r]); R1[r] = fmaf(am, d1, R1[r]);
                     R2[r] = fmaf(am, d2, R2[r]); RD[r] = fmaf(am, dD, RD[r]);
-                    const float u = (cq.w * G[r]) * dLda;      // straight-through alpha clamp: o*G, not alpha
+                    const float u = og[r] * dLda;              // straight-through alpha clamp: o*G, not alpha
                     U0 += u;
                     const float udy = u * dy[r];
                     U1 += udy;
@@ -420,15 +429,15 @@ k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
                 v[2] = -0.5f * dx * dxU0;
                 v[3] = -dx * U1;
                 v[4] = -0.5f * U2;
-                v[5] = __fdividef(U0, cq.w);
+                v[5] = U0 * fast_rcp(cq.w);
                 v[6] = V0; v[7] = V1; v[8] = V2; v[9] = VD;
                 float sum; int slot; bool ok;
                 warp_reduce_scatter10(v, lane, sum, slot, ok);
                 if (ok) atomicAdd(sgrad + (size_t)__float_as_int(a.w) * TGS_NGRAD + slot, sum);
             }
         }
-        __syncthreads();
-        if (tid == 0 && q + 2 < nb) issue(q + 2);
+        __syncwarp();
+        if (lane == 0 && q + 2 < nb) issue(q + 2);
     }
 }
 
@@ -477,7 +486,7 @@ int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, BinView bv, I
         if (mode != TGS_LOSS_NONE && ts == nullptr) { tgs_set_error("touch loss enabled but scale pointer is NULL"); return TGS_EINVAL; }
     }
     TgsProfScope prof(TGS_STAGE_RENDER_BWD, st);
-    k_render_bwd<<<nt, kBwdThreads, 0, st>>>(bv.ranges, bv.records, cam.W, cam.H, cam.Tx, cam.row0, s->bg,
+    k_render_bwd<<<2 * nt, kBwdThreads, 0, st>>>(bv.ranges, bv.records, cam.W, cam.H, cam.Tx, cam.row0, s->bg,
                                      s->depth_normalize, iv.final_T, iv.n_contrib, iv.depth_raw, dL_dcolor,
                                      dL_ddepth, dL_dalpha, tt, tw, ts, mode, residual, screen_grads);
     tgs_count_own(1);
