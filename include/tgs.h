@@ -63,6 +63,13 @@ typedef struct TgsSettings {
     int32_t tile_row_begin;   /* tile-row band rendered by this rank (multi-GPU shard) */
     int32_t tile_row_end;     /* exclusive; (0, ceil(H/16)) = whole image; (0,0) is also whole image */
     int32_t depth_normalize;  /* 1: returned depth = D/alpha (expected depth), 0: raw sum */
+    int32_t reserved0;
+    int64_t rendered_hint;    /* 0: synchronous sizing (read num_rendered, then bin).  > 0: SPECULATIVE mode: the
+                               * binning buffers are sized for this many instances and the binning + render kernels
+                               * are enqueued BEFORE the host waits for the real count (the wait is on an event
+                               * recorded right after the scan, so the GPU always has work queued behind it).
+                               * If the real count exceeds the hint, the tail is re-run with the exact size:
+                               * results are identical in both modes. */
     const float* viewmatrix;  /* [16] device */
     const float* projmatrix;  /* [16] device */
     const float* campos;      /* [3]  device */
@@ -95,6 +102,7 @@ typedef struct TgsSaved {
     void*   binning;       /* TGS_BUF_BINNING */
     void*   image;         /* TGS_BUF_IMAGE   */
     int64_t num_rendered;  /* I */
+    int64_t capacity;      /* instances the binning buffer was laid out for (>= num_rendered) */
 } TgsSaved;
 
 /* Gradient outputs of backward (all device, fully written by the kernels: no memset needed). */

@@ -468,3 +468,39 @@ def test_fullsize_determinism_linearity_and_bands(c3_state):
         acc_m += gmb
         acc_o += gob
     assert rel_inf(acc_m, gm1) < 1e-4 and rel_inf(acc_o, go1) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["c1", "ragged", "band"])        # c1: T = 64 = 2^6 exercises the pad-key bit
+@pytest.mark.parametrize("hint_scale", [0.3, 1.0, 1.7])           # overflow (exact re-run) / exact / slack
+def test_speculative_sizing_is_bit_identical(name, hint_scale):
+    """rendered_hint only changes WHEN the host learns num_rendered, never the result."""
+    c, sc, cam = _case(name)
+    band = c.get("band")
+    rs = cuda_settings(cam, c["deg"], DEV, (0.1, 0.2, 0.3), c.get("mod", 1.0))
+    m, s, r, o, sh = _to(DEV, sc.means3D, sc.scales, sc.rotations, sc.opacities, sc.shs)
+    ref = T.inspect_state.forward_state(m, o, rs, shs=sh, scales=s, rotations=r, opt=T.TouchOptions(tile_rows=band))
+    I = ref["num_rendered"]
+    hint = max(1, int(I * hint_scale))
+    got = T.inspect_state.forward_state(m, o, rs, shs=sh, scales=s, rotations=r,
+                                        opt=T.TouchOptions(tile_rows=band, rendered_hint=hint))
+    assert got["num_rendered"] == I
+    for k in ("color", "depth", "alpha", "radii", "ranges"):
+        assert torch.equal(got[k], ref[k]), k
+    y0, y1 = (0, c["H"]) if band is None else T.sharding.band_pixel_rows(band, c["H"])
+    for k in ("final_T", "n_contrib"):            # per-pixel saved state exists only inside the band
+        assert torch.equal(got[k][y0:y1], ref[k][y0:y1]), k
+    assert torch.equal(got["keys"][:I], ref["keys"][:I]) and torch.equal(got["vals"][:I], ref["vals"][:I])
+    assert torch.equal(got["records"][:I], ref["records"][:I])
+    # and the backward through the operator agrees too
+    H, W = c["H"], c["W"]
+    g = torch.Generator().manual_seed(2)
+    grgb = (torch.rand(3, H, W, generator=g) / (3 * H * W)).to(DEV)
+
+    def grads(h):
+        mm = m.clone().requires_grad_(True)
+        ras = T.GaussianRasterizer(rs)
+        color = ras(mm, None, o, shs=sh, scales=s, rotations=r, tile_rows=band, rendered_hint=h)[0]
+        (color * grgb).sum().backward()
+        assert ras.last_num_rendered == I
+        return mm.grad
+    assert rel_inf(grads(hint), grads(0)) < 1e-5

@@ -27,7 +27,7 @@ class TgsSettings(C.Structure):
         ("sh_degree", C.c_int32), ("sh_coeffs", C.c_int32),
         ("prefiltered", C.c_int32), ("debug", C.c_int32),
         ("tile_row_begin", C.c_int32), ("tile_row_end", C.c_int32),
-        ("depth_normalize", C.c_int32),
+        ("depth_normalize", C.c_int32), ("reserved0", C.c_int32), ("rendered_hint", C.c_int64),
         ("viewmatrix", c_fp), ("projmatrix", c_fp), ("campos", c_fp), ("bg", c_fp),
     ]
 
@@ -45,7 +45,8 @@ class TgsTouch(C.Structure):
 
 
 class TgsSaved(C.Structure):
-    _fields_ = [("geom", c_fp), ("binning", c_fp), ("image", c_fp), ("num_rendered", C.c_int64)]
+    _fields_ = [("geom", c_fp), ("binning", c_fp), ("image", c_fp), ("num_rendered", C.c_int64),
+                ("capacity", C.c_int64)]
 
 
 class TgsGrads(C.Structure):

@@ -99,7 +99,7 @@ extern "C" int tgs_geom_layout(int32_t N, TgsGeomLayout* o) {
 }
 extern "C" int tgs_binning_layout(int64_t I, int32_t T, TgsBinningLayout* o) {
     Carver c; size_t n = (size_t)(I > 0 ? I : 0);
-    o->key_bytes = T <= 65536 ? 2 : 4;
+    o->key_bytes = T < 65535 ? 2 : 4;
     o->ranges = c.take((size_t)(T > 0 ? T : 1) * sizeof(uint2));
     o->records = c.take(n * sizeof(TgsRecord));
     o->tile_sorted = c.take(n * o->key_bytes);
@@ -173,6 +173,12 @@ static int check_inputs(const TgsSettings* s, const TgsGaussians* g) {
     return 0;
 }
 
+static cudaEvent_t count_event() {
+    static thread_local cudaEvent_t ev = nullptr;
+    if (!ev) { if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) ev = nullptr; }
+    return ev;
+}
+
 static uint32_t* pinned_word() {
     static thread_local uint32_t* p = nullptr;
     if (!p) { if (cudaHostAlloc((void**)&p, 64, cudaHostAllocDefault) != cudaSuccess) p = nullptr; }
@@ -212,25 +218,44 @@ extern "C" int tgs_forward(const TgsSettings* s, const TgsGaussians* g, tgs_allo
     GeomView gv = tgs_geom_view(geom, N);
     ImageView iv = tgs_image_view(image, cam.W, cam.H);
 
-    int64_t I = 0;
+    if ((touch_target == nullptr) != (residual_out == nullptr)) { tgs_set_error("touch_target and residual_out go together"); return TGS_EINVAL; }
+    int64_t I = 0, cap = 0;
+    void* binning = nullptr;
+    uint32_t* hp = pinned_word();
+    if (!hp) { tgs_set_error("cudaHostAlloc failed"); return TGS_ENOMEM; }
+    auto tail = [&](int64_t count, int64_t capacity, bool spec) -> int {      // bin + render for `capacity` slots
+        TgsBinningLayout bl; tgs_binning_layout(capacity, T, &bl);
+        binning = alloc(user, TGS_BUF_BINNING, bl.total);
+        if (!binning) { tgs_set_error("allocator returned NULL"); return TGS_ENOMEM; }
+        BinView bv = tgs_bin_view(binning, capacity, T);
+        int r = tgs_emit_sort_pack(gv, bv, N, count, capacity, spec, T, cam.Tx, st); if (r) return r;
+        if (s->debug) TGS_CUDA(cudaStreamSynchronize(st));
+        return tgs_launch_render_fwd(cam, s, bv, iv, out_color, out_depth, out_alpha, touch_target, residual_out, st);
+    };
     if (N > 0) {
         rc = tgs_launch_preprocess(cam, s, g, gv, radii, st); if (rc) return rc;
         rc = tgs_depth_order_and_scan(gv, N, st); if (rc) return rc;
-        uint32_t* hp = pinned_word();
-        if (!hp) { tgs_set_error("cudaHostAlloc failed"); return TGS_ENOMEM; }
         TGS_CUDA(cudaMemcpyAsync(hp, gv.offsets + (N - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        TGS_CUDA(cudaStreamSynchronize(st));   // the one host sync of the forward
-        I = (int64_t)*hp;
+        if (s->rendered_hint > 0) {
+            // SPECULATIVE: enqueue binning + render for `hint` slots, THEN wait for the count (event recorded
+            // right after the scan: the GPU keeps working on the speculative tail while the host wakes up)
+            cudaEvent_t ev = count_event();
+            if (!ev) { tgs_set_error("cudaEventCreate failed"); return TGS_ENOMEM; }
+            TGS_CUDA(cudaEventRecord(ev, st));
+            cap = s->rendered_hint;
+            rc = tail(cap, cap, true); if (rc) return rc;
+            TGS_CUDA(cudaEventSynchronize(ev));
+            I = (int64_t)*hp;
+            if (I > cap) { cap = I; rc = tail(I, I, false); if (rc) return rc; }   // hint too small: exact re-run
+        } else {
+            TGS_CUDA(cudaStreamSynchronize(st));   // the one host sync of the forward
+            I = (int64_t)*hp; cap = I;
+            rc = tail(I, I, false); if (rc) return rc;
+        }
+    } else {
+        rc = tail(0, 0, false); if (rc) return rc;
     }
-    TgsBinningLayout bl; tgs_binning_layout(I, T, &bl);
-    void* binning = alloc(user, TGS_BUF_BINNING, bl.total);
-    if (!binning) { tgs_set_error("allocator returned NULL"); return TGS_ENOMEM; }
-    BinView bv = tgs_bin_view(binning, I, T);
-    rc = tgs_emit_sort_pack(gv, bv, N, I, T, cam.Tx, st); if (rc) return rc;
-    if (s->debug) TGS_CUDA(cudaStreamSynchronize(st));
-    if ((touch_target == nullptr) != (residual_out == nullptr)) { tgs_set_error("touch_target and residual_out go together"); return TGS_EINVAL; }
-    rc = tgs_launch_render_fwd(cam, s, bv, iv, out_color, out_depth, out_alpha, touch_target, residual_out, st); if (rc) return rc;
-    saved->geom = geom; saved->binning = binning; saved->image = image; saved->num_rendered = I;
+    saved->geom = geom; saved->binning = binning; saved->image = image; saved->num_rendered = I; saved->capacity = cap;
     return 0;
 }
 
@@ -243,7 +268,7 @@ extern "C" int tgs_backward_render(const TgsSettings* s, const TgsGaussians* g, 
     if (!dL_dcolor || (g->N > 0 && !screen_grads)) { tgs_set_error("tgs_backward_render: NULL gradient buffers"); return TGS_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
     const TgsCam cam = tgs_make_cam(s);
-    BinView bv = tgs_bin_view(saved->binning, saved->num_rendered, cam.Tx * cam.Ty);
+    BinView bv = tgs_bin_view(saved->binning, saved->capacity > 0 ? saved->capacity : saved->num_rendered, cam.Tx * cam.Ty);
     ImageView iv = tgs_image_view(saved->image, cam.W, cam.H);
     if (g->N > 0) TGS_CUDA(cudaMemsetAsync(screen_grads, 0, sizeof(float) * TGS_NGRAD * (size_t)g->N, st));
     return tgs_launch_render_bwd(cam, s, bv, iv, dL_dcolor, dL_ddepth, dL_dalpha, touch, residual_out, screen_grads, st);

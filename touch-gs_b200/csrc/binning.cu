@@ -33,7 +33,7 @@ using TilesIt = cub::TransformInputIterator<uint32_t, TilesInOrder, cub::Countin
 template <typename KeyT>
 __global__ void __launch_bounds__(256)
 k_emit(int N, const uint32_t* __restrict__ order, const uint32_t* __restrict__ tiles,
-       const uint32_t* __restrict__ offsets, const uint2* __restrict__ rect, int Tx,
+       const uint32_t* __restrict__ offsets, const uint2* __restrict__ rect, int Tx, uint32_t cap,
        KeyT* __restrict__ keys, uint32_t* __restrict__ vals) {
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * blockDim.x + threadIdx.x;          // depth rank
@@ -56,8 +56,10 @@ k_emit(int N, const uint32_t* __restrict__ order, const uint32_t* __restrict__ t
         const uint32_t base = gend - gcnt;
         for (uint32_t t = lane; t < gcnt; t += 32) {
             const uint32_t yy = t / w, xx = t - yy * w;              // row-major: y outer, x inner
-            keys[base + t] = (KeyT)((y0 + yy) * Tx + x0 + xx);
-            vals[base + t] = gid;
+            if (base + t < cap) {                                    // speculative mode: never write past the hint
+                keys[base + t] = (KeyT)((y0 + yy) * Tx + x0 + xx);
+                vals[base + t] = gid;
+            }
         }
     }
 }
@@ -68,10 +70,16 @@ k_emit(int N, const uint32_t* __restrict__ order, const uint32_t* __restrict__ t
 // a single TMA bulk store.
 template <typename KeyT>
 __global__ void __launch_bounds__(256)
-k_pack_ranges(int64_t I, const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals,
-              const float4* __restrict__ rec_in, float4* __restrict__ rec_out, uint2* __restrict__ ranges) {
+k_pack_ranges(int64_t I_host, const uint32_t* __restrict__ I_dev, int64_t cap, const KeyT* __restrict__ keys,
+              const uint32_t* __restrict__ vals, const float4* __restrict__ rec_in, float4* __restrict__ rec_out,
+              uint2* __restrict__ ranges) {
     __shared__ __align__(128) float4 sm[256 * 3];
+    // exact mode: I_host; speculative mode: the real count lives on the device (last scan element), clamped
+    // to the buffer capacity (an overflowing speculation is discarded and re-run by the host)
+    int64_t I = I_host;
+    if (I_dev) { I = (int64_t)*I_dev; if (I > cap) I = cap; }
     const int64_t j0 = (int64_t)blockIdx.x * 256;
+    if (j0 >= I) return;
     const int64_t j = j0 + threadIdx.x;
     if (j < I) {
         const uint32_t id = vals[j];
@@ -101,12 +109,16 @@ k_pack_ranges(int64_t I, const KeyT* __restrict__ keys, const uint32_t* __restri
 }
 
 template <typename KeyT>
-int emit_sort_pack(GeomView gv, BinView bv, int N, int64_t I, int T, int Tx, int tile_bits, cudaStream_t st) {
+int emit_sort_pack(GeomView gv, BinView bv, int N, int64_t I, int64_t cap, bool spec, int T, int Tx, int tile_bits,
+                   cudaStream_t st) {
     KeyT* ku = reinterpret_cast<KeyT*>(bv.tile_unsorted);
     KeyT* ks = reinterpret_cast<KeyT*>(bv.tile_sorted);
     {
         TgsProfScope prof(TGS_STAGE_DUPLICATE, st);
-        k_emit<KeyT><<<(N + 255) / 256, 256, 0, st>>>(N, gv.order, gv.tiles_touched, gv.offsets, gv.rect, Tx, ku,
+        // speculative mode sorts `cap` slots: the unused tail must sort behind every real tile id
+        if (spec) TGS_CUDA(cudaMemsetAsync(ku, 0xFF, sizeof(KeyT) * (size_t)cap, st));
+        k_emit<KeyT><<<(N + 255) / 256, 256, 0, st>>>(N, gv.order, gv.tiles_touched, gv.offsets, gv.rect, Tx,
+                                                      (uint32_t)(cap > 0xFFFFFFFFll ? 0xFFFFFFFFll : cap), ku,
                                                       bv.vals_unsorted);
         tgs_count_own(1);
         TGS_CUDA(cudaGetLastError());
@@ -121,8 +133,8 @@ int emit_sort_pack(GeomView gv, BinView bv, int N, int64_t I, int T, int Tx, int
     {
         TgsProfScope prof(TGS_STAGE_PACK, st);
         k_pack_ranges<KeyT><<<(unsigned)((I + 255) / 256), 256, 0, st>>>(
-            I, ks, bv.vals_sorted, reinterpret_cast<const float4*>(gv.records), reinterpret_cast<float4*>(bv.records),
-            bv.ranges);
+            I, spec ? gv.offsets + (N - 1) : nullptr, cap, ks, bv.vals_sorted,
+            reinterpret_cast<const float4*>(gv.records), reinterpret_cast<float4*>(bv.records), bv.ranges);
         tgs_count_own(1);
         TGS_CUDA(cudaGetLastError());
     }
@@ -143,7 +155,7 @@ size_t tgs_depth_sort_temp_bytes(int N) {
 
 size_t tgs_tile_sort_temp_bytes(int64_t I, int T) {
     size_t bytes = 0;
-    if (T <= 65536)
+    if (T < 65535)
         cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint16_t*)nullptr, (uint16_t*)nullptr,
                                         (const uint32_t*)nullptr, (uint32_t*)nullptr, I, 0, 16);
     else
@@ -166,11 +178,13 @@ int tgs_depth_order_and_scan(GeomView gv, int N, cudaStream_t st) {
     return 0;
 }
 
-int tgs_emit_sort_pack(GeomView gv, BinView bv, int N, int64_t I, int T, int Tx, cudaStream_t st) {
+int tgs_emit_sort_pack(GeomView gv, BinView bv, int N, int64_t count, int64_t cap, bool speculative, int T, int Tx,
+                       cudaStream_t st) {
     TGS_CUDA(cudaMemsetAsync(bv.ranges, 0, sizeof(uint2) * (size_t)T, st));
-    if (I == 0) return 0;
+    if (count == 0 || N == 0) return 0;
     int bits = 1;
     while ((1 << bits) < T) ++bits;
-    if (T <= 65536) return emit_sort_pack<uint16_t>(gv, bv, N, I, T, Tx, bits, st);
-    return emit_sort_pack<uint32_t>(gv, bv, N, I, T, Tx, bits, st);
+    if (speculative && (1 << bits) == T) ++bits;     // the all-ones pad key must compare above every tile id
+    if (T < 65535) return emit_sort_pack<uint16_t>(gv, bv, N, count, cap, speculative, T, Tx, bits, st);
+    return emit_sort_pack<uint32_t>(gv, bv, N, count, cap, speculative, T, Tx, bits > 32 ? 32 : bits, st);
 }

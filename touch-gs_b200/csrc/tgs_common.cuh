@@ -86,7 +86,10 @@ int tgs_launch_preprocess_bwd(const TgsCam& cam, const TgsSettings* s, const Tgs
 int tgs_launch_mark_visible(int N, const float* means, const float* vm, uint8_t* present, cudaStream_t st);
 // binning.cu
 int tgs_depth_order_and_scan(GeomView gv, int N, cudaStream_t st);
-int tgs_emit_sort_pack(GeomView gv, BinView bv, int N, int64_t I, int T, int Tx, cudaStream_t st);
+// `cap` = instances the binning buffer holds; `count` = instances to sort (== I in exact mode, == cap in
+// speculative mode, where the real count is read on the device from gv.offsets[N-1])
+int tgs_emit_sort_pack(GeomView gv, BinView bv, int N, int64_t count, int64_t cap, bool speculative, int T, int Tx,
+                       cudaStream_t st);
 // render.cu
 int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, BinView bv, ImageView iv,
                           float* out_color, float* out_depth, float* out_alpha,

@@ -47,11 +47,12 @@ def forward_state(means3D, opacities, rs: GaussianRasterizationSettings, shs=Non
     geom, binning, image = ctx.saved[-3], ctx.saved[-2], ctx.saved[-1]
     N = int(means3D.shape[0])
     I = ctx.num_rendered
+    cap = getattr(ctx, 'capacity', I) or I
     H, W = rs.image_height, rs.image_width
     Tx, Ty = (W + TILE - 1) // TILE, (H + TILE - 1) // TILE
     gl, bl, il = L.TgsGeomLayout(), L.TgsBinningLayout(), L.TgsImageLayout()
     lib.tgs_geom_layout(N, C.byref(gl))
-    lib.tgs_binning_layout(I, Tx * Ty, C.byref(bl))
+    lib.tgs_binning_layout(cap, Tx * Ty, C.byref(bl))
     lib.tgs_image_layout(W, H, C.byref(il))
     rec = _view(geom, gl.records, N * 12, torch.float32).view(N, 12)
     rect = _view(geom, gl.rect, N * 2, torch.int32).view(N, 2)

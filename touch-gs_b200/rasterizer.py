@@ -54,6 +54,8 @@ class TouchOptions(NamedTuple):
     depth_loss_norm: Optional[float] = None        # Z; None -> #(touch_depth > 0)
     tile_rows: Optional[Tuple[int, int]] = None    # tile-row band of this rank
     process_group: object = None                   # all-reduce group for the screen-space gradients
+    rendered_hint: int = 0                         # > 0: speculative sizing (hides the forward's host sync)
+    info: Optional[dict] = None                    # filled with num_rendered / capacity of the call
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -120,7 +122,8 @@ def _make_settings(rs: GaussianRasterizationSettings, opt: TouchOptions, K: int,
         tanfovx=float(rs.tanfovx), tanfovy=float(rs.tanfovy), scale_modifier=float(rs.scale_modifier),
         sh_degree=int(rs.sh_degree), sh_coeffs=int(K), prefiltered=int(bool(rs.prefiltered)),
         debug=int(bool(rs.debug)), tile_row_begin=r0, tile_row_end=r1,
-        depth_normalize=int(bool(opt.depth_normalize)),
+        depth_normalize=int(bool(opt.depth_normalize)), reserved0=0,
+        rendered_hint=max(0, int(opt.rendered_hint or 0)),
         viewmatrix=vm.data_ptr(), projmatrix=pmx.data_ptr(), campos=cam.data_ptr(), bg=bg.data_ptr())
     return s, (r0, r1, Ty)
 
@@ -200,6 +203,10 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.rs, ctx.opt, ctx.K = rs, opt, K
         ctx.opacity_shape = opacity_shape
         ctx.num_rendered = int(saved.num_rendered)
+        ctx.capacity = int(saved.capacity)
+        if opt.info is not None:
+            opt.info["num_rendered"] = ctx.num_rendered
+            opt.info["capacity"] = ctx.capacity
         ctx.has = (sh is not None, colors_precomp is not None, scales is not None, cov3Ds_precomp is not None)
         ctx.touch = (touch_depth, touch_weight)
         none = torch.empty(0, device=dev)
@@ -231,7 +238,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             s, _ = _make_settings(rs, opt, K, keep)
             g = _make_gaussians(means3D, opacities, sh, colors, scales, rots, cov3D)
             saved = L.TgsSaved(geom=geom.data_ptr(), binning=binning.data_ptr(), image=image.data_ptr(),
-                               num_rendered=ctx.num_rendered)
+                               num_rendered=ctx.num_rendered, capacity=ctx.capacity)
             g_color = torch.zeros((3, H, W), dtype=torch.float32, device=dev) if g_color is None \
                 else _chk(g_color, "grad_color", (3, H, W), dev)
             g_depth = None if g_depth is None else _chk(g_depth.reshape(H, W), "grad_depth", (H, W), dev)
@@ -291,6 +298,7 @@ class GaussianRasterizer(torch.nn.Module):
     def __init__(self, raster_settings: GaussianRasterizationSettings):
         super().__init__()
         self.raster_settings = raster_settings
+        self.last_num_rendered = 0
 
     def markVisible(self, positions: torch.Tensor) -> torch.Tensor:
         """bool[N]: view-space z > 0.2 for the module's camera."""
@@ -310,16 +318,21 @@ class GaussianRasterizer(torch.nn.Module):
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
                 rotations=None, cov3D_precomp=None, *, touch_depth=None, touch_weight=None,
                 depth_loss: str = "none", depth_loss_mult: float = 1.0, depth_normalize: bool = True,
-                depth_loss_norm: Optional[float] = None, tile_rows=None, process_group=None):
+                depth_loss_norm: Optional[float] = None, tile_rows=None, process_group=None,
+                rendered_hint: int = 0):
         if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
             raise Exception("Please provide excatly one of either SHs or precomputed colors!")
         if ((scales is None or rotations is None) and cov3D_precomp is None) or \
                 ((scales is not None or rotations is not None) and cov3D_precomp is not None):
             raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
         e = torch.Tensor([]).to(means3D.device)
+        info = {}
         opt = TouchOptions(touch_depth, touch_weight, depth_loss, depth_loss_mult, depth_normalize,
-                           depth_loss_norm, tile_rows, process_group)
-        return rasterize_gaussians(means3D, means2D,
-                                   e if shs is None else shs, e if colors_precomp is None else colors_precomp,
-                                   opacities, e if scales is None else scales, e if rotations is None else rotations,
-                                   e if cov3D_precomp is None else cov3D_precomp, self.raster_settings, opt)
+                           depth_loss_norm, tile_rows, process_group, rendered_hint, info)
+        out = rasterize_gaussians(means3D, means2D,
+                                  e if shs is None else shs, e if colors_precomp is None else colors_precomp,
+                                  opacities, e if scales is None else scales, e if rotations is None else rotations,
+                                  e if cov3D_precomp is None else cov3D_precomp, self.raster_settings, opt)
+        # instance count of this call: feed it back as `rendered_hint` the next time this view is rendered
+        self.last_num_rendered = info.get("num_rendered", 0)
+        return out
