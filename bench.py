@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cameras", type=int, default=8)
+    ap.add_argument("--workload", default="rasterizer", choices=["rasterizer", "touch_inputs"],
+                    help="touch_inputs: roofline of the per-pixel touch/vision fusion kernel (SURVEY §8f N2), not the headline metric")
     ap.add_argument("--no-hints", action="store_true", help="synchronous sizing in every forward (no rendered_hint)")
     return ap.parse_args()
 
@@ -355,9 +357,43 @@ def run_reference(args, cfg, N):
     print(json.dumps(out), flush=True)
 
 
+def run_touch_inputs(args):
+    """Secondary line: the fp64 per-pixel fusion kernel on a dataset-sized batch (100 frames of 1280x720,
+    the reference's native real-world size -- SURVEY A7), uint16 in / uint16 + fp32 out, 22 B per pixel."""
+    import touchgs_b200 as T
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    n = 100 * 1280 * 720
+    g = torch.Generator(device="cpu").manual_seed(0)
+    mk = lambda hi: torch.randint(0, hi, (n,), generator=g, dtype=torch.int32).to(torch.uint16).to(dev)
+    touch, vision, tsig = mk(3000), mk(6000), mk(60)
+    fn = lambda: T.touch_inputs.fuse_touch_vision(touch, vision, tsig, 1.3, -0.2, 0.017, True, 1.0)
+    for _ in range(max(args.warmup, 3)):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    peak, src = peaks()
+    gbs = 22.0 * n / (ms * 1e-3) / 1e9
+    print(json.dumps({"metric": "touch/vision fusion pixels/s (secondary; SURVEY 8f N2)", "value": n / (ms * 1e-3), "unit": "pixels/s",
+                      "ms_per_step": ms, "steps": args.steps, "dtype": "f64 math, u16/f32 I/O", "data": "synthetic",
+                      "config": {"workload": "100 frames x 1280x720 uint16 (touch depth, vision depth, touch sigma)",
+                                 "note": "includes 6 torch.empty output allocations per call; 737 MB working set > L2"},
+                      "roofline": {"bound": "hbm", "kernel": "k_fuse_touch_vision", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                                   "frac": gbs / peak, "traffic": None, "peak_source": src,
+                                   "algorithmic_bytes_per_launch": 22 * n}}), flush=True)
+
+
 # --------------------------------------------------------------------------------- main
 def main():
     args = parse()
+    if args.workload == "touch_inputs":
+        run_touch_inputs(args)
+        return
     import touchgs_b200 as T
     cfg = dict(T.synth.CONFIGS[args.config])
     N = args.num_gaussians or cfg["N"]

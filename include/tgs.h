@@ -193,6 +193,22 @@ int tgs_touch_loss_scale(const float* target, int64_t num_pixels, float mult, fl
                          float* scale_out, void* stream);
 
 /*
+ * SURVEY §8(f) N2 -- the per-pixel part of the reference's touch / vision depth fusion, fp64, bit-identical
+ * to the uint16 PNGs the reference writes.  Replaces (per image) reference utils/fuse_touch_vision.py
+ * :270-276 (uint16-mm decode), :288-306 (apply the fitted alignment: scale/offset from the first fit,
+ * offset2 from the second), :310-313 (vision sigma = clip(0.05*depth,0,10)+5), :76-202 (inverse-variance
+ * fusion), :360-361 (clips), :373-376 (uint16 encode) and the trainer-side decode (reference
+ * legacy/dataparser_tactile.py:65-66): target = mm*1e-3*scene_scale, weight = 1/sigma (0 where sigma = 0).
+ * Inputs / uint16 outputs: device, 8-byte aligned; target / weight: device fp32, 16-byte aligned.
+ * Any output pointer may be NULL.
+ */
+int tgs_fuse_touch_vision(const uint16_t* touch_mm, const uint16_t* vision_mm, const uint16_t* touch_sigma_mm,
+                          int64_t num_pixels, double scale, double offset, double offset2,
+                          int32_t is_real_world, double scene_scale,
+                          uint16_t* vision_aligned_mm, uint16_t* ds_gs_mm, uint16_t* fused_mm,
+                          uint16_t* fused_sigma_mm, float* target, float* weight, void* stream);
+
+/*
  * Host-buffer entry point (the call a non-PyTorch trainer makes; timed by the end-to-end bench with
  * every host<->device copy inside the timed region).  EVERY pointer reachable from s_host / g_host /
  * grads_host and every *_host argument is a HOST pointer (NULL = absent / not wanted).  The call

@@ -23,8 +23,8 @@ def host_math_lib():
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "libhostmath.so")
     src = os.path.join(ROOT, "tests", "host_math_harness.cpp")
-    hdr = os.path.join(ROOT, "touch-gs_b200", "csrc", "tgs_math.cuh")
-    if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(ROOT, "touch-gs_b200", "csrc", h) for h in ("tgs_math.cuh", "touch_inputs_math.cuh")]
+    if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(p) for p in [src] + hdrs):
         subprocess.run(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, src], check=True)
     return ctypes.CDLL(so)
 

@@ -3,6 +3,7 @@
 // Built by tests/conftest.py with: g++ -O1 -ffp-contract=off -shared -fPIC.
 // Never linked into libtgs.so; the product path is CUDA only.
 #include "../touch-gs_b200/csrc/tgs_math.cuh"
+#include "../touch-gs_b200/csrc/touch_inputs_math.cuh"
 
 extern "C" {
 
@@ -61,6 +62,17 @@ void hm_backward(int N, const float* means, const float* scales, const float* ro
         for (int k = 0; k < 3; ++k) { dmeans[3 * i + k] = dm[k]; dscales[3 * i + k] = ds[k]; }
         for (int k = 0; k < 4; ++k) drots[4 * i + k] = dq[k];
         for (int k = 0; k < 6; ++k) dcov_out[6 * i + k] = dc[k];
+    }
+}
+
+// per-pixel touch / vision fusion (fp64) on the host: out6 = va, ds, fu, fs (uint16) ; target, weight (float)
+void hm_fuse(long n, const unsigned short* touch, const unsigned short* vision, const unsigned short* tsig,
+             double scale, double offset, double offset2, int real_world, double scene_scale,
+             unsigned short* va, unsigned short* ds, unsigned short* fu, unsigned short* fs, float* target, float* weight) {
+    FuseParams p; p.scale = scale; p.offset = offset; p.offset2 = offset2; p.unit = 1e-3 * scene_scale; p.real_world = real_world;
+    for (long i = 0; i < n; ++i) {
+        PixelOut o = fuse_pixel(touch[i], vision[i], tsig[i], p);
+        va[i] = o.va; ds[i] = o.ds; fu[i] = o.fu; fs[i] = o.fs; target[i] = o.target; weight[i] = o.weight;
     }
 }
 

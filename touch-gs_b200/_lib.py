@@ -91,6 +91,8 @@ SIGNATURES = {
     "tgs_backward": (C.c_int, [C.POINTER(TgsSettings), C.POINTER(TgsGaussians), C.POINTER(TgsSaved), c_fp,
                                c_fp, c_fp, c_fp, C.POINTER(TgsTouch), c_fp, c_fp, C.POINTER(TgsGrads), c_fp]),
     "tgs_touch_loss_scale": (C.c_int, [c_fp, C.c_int64, C.c_float, C.c_float, c_fp, c_fp]),
+    "tgs_fuse_touch_vision": (C.c_int, [c_fp, c_fp, c_fp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_int32,
+                                        C.c_double, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "tgs_train_step_host": (C.c_int, [C.POINTER(TgsSettings), C.POINTER(TgsGaussians), c_fp, c_fp, c_fp,
                                       C.c_int32, C.c_float, C.POINTER(TgsGrads), c_fp, c_fp, c_fp, c_fp,
                                       C.POINTER(C.c_int64), c_fp]),

@@ -27,6 +27,7 @@ UNITS = {
     "render.cu": [],
     "api.cu": [],
     "host_step.cu": [],
+    "touch_inputs.cu": ["--fmad=false"],
 }
 
 
