@@ -515,6 +515,13 @@ def main():
         "preprocess": N * (4 * (11 + 3 * K) + 48 + 8), "preprocess_bwd": N * (4 * (11 + 3 * K) * 2 + 48),
     }[dom]
     dom_ms = stage_ms[dom][0]
+    traffic = None          # DRAM bytes of the dominant kernel from the committed ncu capture (c3, camera 0)
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if args.config == "c3" and world == 1 and dom in tj:
+            traffic = tj[dom]["dram_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        pass
     achieved = per_launch_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     T_band = Tx * (Ty if band is None else band[1] - band[0])
     step_bytes = alg_bytes(N, I_cam0, P_band, T_band, K)
@@ -533,7 +540,7 @@ def main():
         "gpu_launches_detail": {"own_kernels": own, "cub_calls": cub, "per_step": (own + cub) / steps},
         "stage_ms_per_launch": {k: round(v[0], 4) for k, v in stage_ms.items()},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": per_launch_bytes, "launch_ms": dom_ms},
         "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved_GBps": step_bytes / (ms / steps * 1e-3) / 1e9,
                           "frac": step_bytes / (ms / steps * 1e-3) / 1e9 / peak},

@@ -38,7 +38,7 @@ if os.path.exists(path):
         a[1] += v
     tot = sum(a[1] for a in agg.values())
     w(f"# {tag}: ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache serialised: compare SHARES)")
-    w("command: python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --cameras 2   (first 400 launches)")
+    w("command: python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --cameras 1   (first 400 launches; every launch is camera 0)")
     w()
     w("| kernel | launches | total us | share |")
     w("|---|---:|---:|---:|")

@@ -504,3 +504,36 @@ def test_speculative_sizing_is_bit_identical(name, hint_scale):
         assert ras.last_num_rendered == I
         return mm.grad
     assert rel_inf(grads(hint), grads(0)) < 1e-5
+
+
+def test_config_c2_full_parity():
+    """BASELINE config c2 at FULL size (100k Gaussians, 800x800, SH degree 3) with the fused touch depth-L1
+    loss: integer state bit-exact, images and all five gradient tensors within 1e-4 of the oracle."""
+    cfg = synth.CONFIGS["c2"]
+    sc = synth.make_scene(cfg["N"], cfg["sh_degree"], cfg["smin"], cfg["smax"], seed=0)
+    cam = synth.orbit_cameras(cfg["W"], cfg["H"], 8, 3.0, 0)[0]
+    H, W = cfg["H"], cfg["W"]
+    g = torch.Generator().manual_seed(12)
+    grgb = (torch.rand(3, H, W, generator=g) - 0.5) / (3 * H * W)
+    # touch target from a depth render of the perturbed scene by the CUDA path itself (as bench.py does)
+    rs = cuda_settings(cam, cfg["sh_degree"], DEV)
+    pert = synth.perturbed(sc, 0.01, 0)
+    with torch.no_grad():
+        d = T.GaussianRasterizer(rs)(*_to(DEV, pert.means3D), None, *_to(DEV, pert.opacities), shs=pert.shs.to(DEV),
+                                     scales=pert.scales.to(DEV), rotations=pert.rotations.to(DEV))[2]
+    tgt, wgt = synth.make_touch_maps(d[0].cpu(), seed=0)
+    touch = dict(touch_depth=tgt, touch_weight=wgt, depth_loss="l1", depth_loss_mult=0.2, depth_normalize=True)
+    ref_out, ref = _oracle_grads(sc, cam, cfg["sh_degree"], (0, 0, 0), 1.0, grgb, touch)
+    m, s, r, o, sh = _to(DEV, sc.means3D, sc.scales, sc.rotations, sc.opacities, sc.shs)
+    st = T.inspect_state.forward_state(m, o, rs, shs=sh, scales=s, rotations=r)
+    assert torch.equal(st["radii"].cpu(), ref_out.radii)
+    assert torch.equal(st["keys"].cpu(), ref_out.bins.keys) and torch.equal(st["vals"].cpu(), ref_out.bins.vals)
+    assert torch.equal(st["ranges"].cpu(), ref_out.bins.ranges)
+    assert float((st["n_contrib"].cpu() != ref_out.img.n_contrib).float().mean()) <= 2e-3
+    out, got = _cuda_grads(sc, cam, cfg["sh_degree"], (0, 0, 0), 1.0, grgb, touch)
+    budget = 20.0 / (H * W)
+    assert_close_tensor(out[0].cpu(), ref_out.color, "color", 1e-4, budget)
+    assert_close_tensor(out[2].cpu(), ref_out.depth, "depth", 1e-4, budget)
+    assert_close_tensor(out[3].cpu(), ref_out.alpha, "alpha", 1e-4, budget)
+    for k in ("means3D", "scales", "rotations", "opacities", "shs"):
+        assert_close_tensor(got[k], ref[k], "grad_" + k, 1e-4, 2e-3, 5e-3)

@@ -33,16 +33,14 @@ TGS_FHD PixelOut fuse_pixel(unsigned short touch_mm, unsigned short vision_mm,
     if (t2a > 0.0) v = v + p.offset2;                         // :298,:304
     v = fmax(v, 0.0);                                         // :306
     const double vs = fmin(fmax(v * 0.05, 0.0), 10.0) + 5.0;  // create_uncertainty_from_depth.py:21, :312-313
-    const double m = (ts > 0.0) ? 1.0 : 0.0;                  // :109
-    double rv = 1.0 / vs, rt = 1.0 / ts;                      // :116-117
-    if (isinf(rt)) rt = 0.0;                                  // :120
-    if (isinf(rv)) rv = 0.0;                                  // :121
-    double sigma = 1.0 / (rt + rv);                           // :124
-    if (isinf(sigma)) sigma = 0.0;                            // :126
-    double mu_t = (t * m) / ts;                               // :136,:140
-    if (isnan(mu_t)) mu_t = 0.0;                              // :141
-    double mu_v = v / vs;                                     // :143
-    if (isnan(mu_v)) mu_v = 0.0;                              // :144
+    // vs is always in [5, 15]: 1/vs and v/vs are finite, the reference's inf / nan patches (:121,:144) never fire.
+    const double rv = 1.0 / vs;                               // :116
+    const double mu_v = v / vs;                               // :143
+    // touch side.  ts == 0 (no touch here: ~90 % of the pixels): mask = 0, 1/0 = inf -> 0 (:117,:120) and
+    // (t*0)/0 = nan -> 0 (:136-141), so both divisions can be skipped with identical results.
+    double rt = 0.0, mu_t = 0.0;
+    if (ts > 0.0) { rt = 1.0 / ts; mu_t = (t * 1.0) / ts; }   // :109,:117,:136,:140 (finite: no patch fires)
+    double sigma = 1.0 / (rt + rv);                           // :124  (rt + rv >= 1/15 > 0: never inf, :126)
     double fused = sigma * (mu_t + mu_v);                     // :146
     fused = fmax(fused, 0.0);                                 // :360
     sigma = fmin(fmax(sigma, 0.0), 10.0);                     // :361
