@@ -262,6 +262,36 @@ int tgs_geom_layout(int32_t N, TgsGeomLayout* out);
 int tgs_binning_layout(int64_t num_rendered, int32_t num_tiles, TgsBinningLayout* out);
 int tgs_image_layout(int32_t W, int32_t H, TgsImageLayout* out);
 
+/*
+ * "Reference-structure CUDA" comparison arm (BASELINE.md §3 column 2; SURVEY.md §8d "Reference CUDA path beside
+ * it").  The reference's own rasterizer is not in its tree (reference .gitmodules:7-9), so the comparison is the
+ * same algorithm in the upstream kernels' structure, written from the spec: id-order scan + blocking count read,
+ * per-Gaussian 64-bit key emission, ONE 12-byte-pair radix sort, 16x16 one-pixel-per-thread compositing with
+ * gathered per-Gaussian data and no culling, ten per-thread global atomics per (pixel, Gaussian) pair in backward,
+ * touch-depth loss NOT fused (the caller forms dL/ddepth_raw and dL/dalpha).  Used by bench.py and the full-size
+ * cross-check tests only; the operator never calls it.  out_depth_raw = sum depth*alpha*T (un-normalised).
+ * saved->geom / image have the layouts of tgs_geom_layout / tgs_image_layout (tgs_backward_preprocess accepts
+ * them); saved->binning has the layout below.  Whole image only (no tile-row band).
+ */
+typedef struct TgsRefBinningLayout {
+    size_t offsets;        /* uint32[N] inclusive scan of tiles_touched in Gaussian-id order */
+    size_t keys_unsorted;  /* uint64[I] (tile << 32) | bits(depth), emission order */
+    size_t keys_sorted;    /* uint64[I] */
+    size_t vals_unsorted;  /* uint32[I] */
+    size_t vals_sorted;    /* uint32[I] */
+    size_t ranges;         /* uint32[T,2] */
+    size_t temp;
+    size_t temp_bytes;
+    size_t total;
+} TgsRefBinningLayout;
+int tgs_refstructure_binning_layout(int32_t N, int64_t num_rendered, int32_t num_tiles, TgsRefBinningLayout* out);
+int tgs_refstructure_forward(const TgsSettings* s, const TgsGaussians* g, tgs_alloc_fn alloc, void* alloc_user,
+                             float* out_color, float* out_depth_raw, float* out_alpha, int32_t* radii,
+                             TgsSaved* saved, void* stream);
+int tgs_refstructure_backward_render(const TgsSettings* s, const TgsGaussians* g, const TgsSaved* saved,
+                                     const float* dL_dcolor, const float* dL_ddepth_raw, const float* dL_dalpha,
+                                     float* screen_grads, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

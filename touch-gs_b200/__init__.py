@@ -8,7 +8,7 @@ the hyphen); use ``import touchgs_b200`` (top-level shim) or ``import diff_gauss
 from . import _lib
 from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, TouchOptions,
                          rasterize_gaussians, _RasterizeGaussians)
-from . import synth, sharding, inspect_state, touch_inputs
+from . import synth, sharding, inspect_state, touch_inputs, refstructure
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "TouchOptions", "rasterize_gaussians",
-           "synth", "sharding", "inspect_state", "touch_inputs", "_lib"]
+           "synth", "sharding", "inspect_state", "touch_inputs", "refstructure", "_lib"]

@@ -72,6 +72,12 @@ class TgsImageLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in ("final_T", "n_contrib", "depth_raw", "total")]
 
 
+class TgsRefBinningLayout(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in
+                ("offsets", "keys_unsorted", "keys_sorted", "vals_unsorted", "vals_sorted", "ranges", "temp",
+                 "temp_bytes", "total")]
+
+
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int, C.c_size_t)
 
 # every symbol include/tgs.h declares: (restype, argtypes)
@@ -99,6 +105,11 @@ SIGNATURES = {
     "tgs_geom_layout": (C.c_int, [C.c_int32, C.POINTER(TgsGeomLayout)]),
     "tgs_binning_layout": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(TgsBinningLayout)]),
     "tgs_image_layout": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(TgsImageLayout)]),
+    "tgs_refstructure_binning_layout": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.POINTER(TgsRefBinningLayout)]),
+    "tgs_refstructure_forward": (C.c_int, [C.POINTER(TgsSettings), C.POINTER(TgsGaussians), ALLOC_FN, C.c_void_p,
+                                           c_fp, c_fp, c_fp, c_fp, C.POINTER(TgsSaved), c_fp]),
+    "tgs_refstructure_backward_render": (C.c_int, [C.POINTER(TgsSettings), C.POINTER(TgsGaussians),
+                                                   C.POINTER(TgsSaved), c_fp, c_fp, c_fp, c_fp, c_fp]),
 }
 
 _lib = None

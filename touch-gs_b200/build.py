@@ -25,6 +25,7 @@ UNITS = {
     "preprocess.cu": ["--fmad=false"],
     "binning.cu": [],
     "render.cu": [],
+    "refstructure.cu": [],
     "api.cu": [],
     "host_step.cu": [],
     "touch_inputs.cu": ["--fmad=false"],

@@ -24,6 +24,7 @@
 // Roofline: HBM.  Algorithmic bytes: forward 48 B/instance + 24 B/pixel written;
 // backward 48 B/instance read + 40 B/instance accumulated + 32 B/pixel.
 #include "tgs_common.cuh"
+#include "render_math.cuh"
 
 namespace {
 
@@ -64,33 +65,6 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                      smem_u32(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
-}
-
-// power = -0.5*(A dx^2 + C dy^2) - B dx dy with a PINNED rounding sequence: forward and backward must
-// take bit-identical skip decisions (power > 0, alpha < 1/255) for every (pixel, splat) pair, so the
-// contraction into FMAs is spelled out instead of being left to the compiler per kernel.
-__device__ __forceinline__ float splat_power(const float4 q, float dx, float dy) {
-    const float ax = __fmul_rn(q.x, dx);
-    const float cy = __fmul_rn(q.z, dy);
-    const float s = __fmaf_rn(cy, dy, __fmul_rn(ax, dx));
-    const float bxy = __fmul_rn(__fmul_rn(q.y, dx), dy);
-    return __fmaf_rn(-0.5f, s, -bxy);
-}
-__device__ __forceinline__ float splat_alpha(float opacity, float G) {
-    return fminf(TGS_ALPHA_MAX, __fmul_rn(opacity, G));
-}
-// exp(power) = ex2(power*log2e) with flush-to-zero: one FMUL + one MUFU.EX2, no denormal fix-up code.
-// (power <= 0 here; results below 2^-126 flush to 0, far under the 1/255 alpha threshold.)
-__device__ __forceinline__ float splat_exp(float power) {
-    float y;
-    const float x = __fmul_rn(power, 1.4426950408889634f);
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float fast_rcp(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
 }
 
 struct PixelMap {
