@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--num-gaussians", type=int, default=None, help="override N (development only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-refcuda", action="store_true", help="skip the reference-structure CUDA comparison arm")
     ap.add_argument("--cameras", type=int, default=8)
     ap.add_argument("--workload", default="rasterizer", choices=["rasterizer", "touch_inputs"],
                     help="touch_inputs: roofline of the per-pixel touch/vision fusion kernel (SURVEY §8f N2), not the headline metric")
@@ -496,6 +497,37 @@ def main():
                        "double-buffered); loss copied D2H every step and read by the host one step later; Gaussian "
                        "parameters are resident training state"}
 
+    # ---- "reference CUDA path beside it" (SURVEY §8d): the upstream-STRUCTURED kernels (csrc/refstructure.cu) on
+    # the same device, same scene, same cameras, same loss (touch depth-L1 formed in PyTorch, not fused)
+    refcuda = None
+    if world == 1 and not args.no_refcuda:
+        R = T.refstructure
+        rsteps = max(3, min(steps, 16))
+
+        def ref_step(i):
+            b = batches[i % len(batches)]
+            d, cam = b["dev"], b["cam"]
+            rs = T.GaussianRasterizationSettings(H, W, cam.tanfovx, cam.tanfovy, bg, 1.0, d["view"], d["proj"],
+                                                 cfg["sh_degree"], d["campos"], False, False)
+            for v in params.values():
+                v.grad = None
+            color, _, draw, alpha = R.rasterize_refstructure(params["means3D"], params["opacities"], params["shs"],
+                                                             params["scales"], params["rotations"], rs)
+            loss = (color - d["gt"]).abs().sum() * stepper.inv + R.touch_depth_loss_unfused(
+                draw, alpha, d["target"], d["weight"], DEPTH_LOSS_MULT, "l1")
+            loss.backward()
+
+        ms_r, clocks_r, _, _ = timed(ref_step, rsteps, 3)
+        refcuda = {"value": N * rsteps / (ms_r * 1e-3), "unit": UNIT, "ms_per_step": ms_r / rsteps, "steps": rsteps,
+                   "clocks": clocks_r,
+                   "what": "SUBSTITUTE for the reference's own CUDA rasterizer (not in its tree): the same algorithm in "
+                           "the upstream kernels' structure, written from the spec for sm_100a (csrc/refstructure.cu): "
+                           "id-order scan + blocking count read, 64-bit keys, one 12-byte-pair radix sort, 16x16 "
+                           "one-pixel-per-thread compositing without culling, 10 per-thread atomics per (pixel, splat) "
+                           "in backward, touch depth-L1 in PyTorch outside the kernels"}
+        for v in params.values():
+            v.grad = None
+
     if rank != 0:
         if world > 1:
             torch.distributed.barrier()
@@ -547,6 +579,8 @@ def main():
     }
     if e2e is not None:
         out["e2e"] = e2e
+    if refcuda is not None:
+        out["reference_structure_cuda"] = refcuda
     if world == 1 and not args.no_cpu_baseline:
         b0 = batches[0]
         ref = CpuReference(cfg, scene, b0["cam"], b0["host"]["target"].clone(), b0["host"]["weight"].clone())

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TGS_ABI_VERSION 1
+#define TGS_ABI_VERSION 2
 
 #define TGS_EINVAL   (-1)   /* bad argument combination / shape */
 #define TGS_ENOMEM   (-2)   /* allocator callback returned NULL */
@@ -94,6 +94,8 @@ typedef struct TgsTouch {
     const float* weight;   /* [H,W] per-pixel weight (e.g. 1/sigma) or NULL = 1 */
     const float* scale;    /* device scalar: depth_loss_mult / Z  (see tgs_touch_loss_scale) */
     int32_t mode;          /* TGS_LOSS_* */
+    int32_t row_begin;     /* pixel rows [row_begin,row_end) where the loss applies; (0,0) = every row.  A rank of the */
+    int32_t row_end;       /* tile-row shard that renders a halo around its band restricts the loss to its own rows. */
 } TgsTouch;
 
 /* Saved state handed from forward to backward. */
@@ -291,6 +293,83 @@ int tgs_refstructure_forward(const TgsSettings* s, const TgsGaussians* g, tgs_al
 int tgs_refstructure_backward_render(const TgsSettings* s, const TgsGaussians* g, const TgsSaved* saved,
                                      const float* dL_dcolor, const float* dL_ddepth_raw, const float* dL_dalpha,
                                      float* screen_grads, void* stream);
+
+/* ====================================================================================================
+ * SURVEY.md §8(f) row N1 -- the rest of a Touch-GS TRAIN STEP around the rasterizer (BASELINE config c5:
+ * "full Touch-GS train step (Adam + densify)").  The trainer is `ns-train depth-gaussian-splatting`
+ * (reference scripts/train_bunny_real.sh:52) from the reference's EMPTY nerfstudio submodule (reference
+ * .gitmodules:7-9), so these entry points replace the per-step torch ops of that model's loss / optimizer /
+ * refine code as publicly documented for the splat trainers of that era; what the tree
+ * pins: AdamOptimizerConfig(lr=..., eps=1e-15) (reference legacy/config_tactile.py:43-50), 30000 iterations
+ * (reference legacy/config_tactile.py:28), the depth-loss knobs (reference scripts/train_block_data.sh:50).
+ * All pointers are DEVICE pointers unless named *_host.
+ * ==================================================================================================== */
+
+/* floats of scratch tgs_photometric_loss_forward needs (three derivative maps per channel) */
+size_t tgs_photometric_scratch_floats(int32_t W, int32_t H);
+/*
+ * loss = (1-l) * mean|C - C*| + l * (1 - mean SSIM(C, C*)); 11x11 Gaussian window (sigma 1.5), zero padding,
+ * C1 = 0.01^2, C2 = 0.03^2; means over all 3*H*W elements.  color / gt: [3,H,W].  Only rows
+ * [row_begin,row_end) are loss pixels ((0,0) = all): the partial losses of the disjoint bands of a tile-row
+ * shard add up to the full-image loss.  sums: 2 doubles (workspace), loss_out: 1 float.
+ */
+int tgs_photometric_loss_forward(const float* color, const float* gt, int32_t W, int32_t H,
+                                 int32_t row_begin, int32_t row_end, float lambda_dssim, float* dmaps,
+                                 double* sums, float* loss_out, void* stream);
+/* dL_dcolor rows [out_row_begin,out_row_end) <- grad_out[0] (device scalar, NULL = 1) * dloss/dcolor;
+ * pixels within 5 rows of the loss band receive SSIM gradient (the band's halo). */
+int tgs_photometric_loss_backward(const float* color, const float* gt, const float* dmaps, int32_t W, int32_t H,
+                                  int32_t row_begin, int32_t row_end, int32_t out_row_begin, int32_t out_row_end,
+                                  float lambda_dssim, const float* grad_out, float* dL_dcolor, void* stream);
+
+/* raw parameters -> rasterizer inputs: scales = exp(scales_log), rotations = quats/|quats|, opacities = sigmoid */
+int tgs_activate_forward(int32_t N, const float* scales_log, const float* quats, const float* opacity_logit,
+                         float* scales, float* rotations, float* opacities, void* stream);
+/* chain rule of the above; every output may alias the matching d* input */
+int tgs_activate_backward(int32_t N, const float* scales_log, const float* quats, const float* opacity_logit,
+                          const float* dscales, const float* drotations, const float* dopacities,
+                          float* dscales_log, float* dquats, float* dopacity_logit, void* stream);
+
+/* One-launch Adam over up to TGS_ADAM_MAX_GROUPS parameter groups (torch.optim.Adam arithmetic, no weight decay,
+ * no amsgrad).  period > 0: element i uses `lr` when (i % period) < head, else `lr_tail` (one [N,K,3] SH tensor
+ * with the DC / higher-band learning rates of the features_dc / features_rest groups, no torch.cat per step). */
+#define TGS_ADAM_MAX_GROUPS 8
+typedef struct TgsAdamGroup {
+    float* param; const float* grad; float* exp_avg; float* exp_avg_sq;   /* 16-byte aligned */
+    int64_t numel;
+    float lr, lr_tail;
+    int32_t period, head;
+} TgsAdamGroup;
+int tgs_adam_step(const TgsAdamGroup* groups_host, int32_t n_groups, int32_t step, float beta1, float beta2,
+                  float eps, void* stream);
+
+/* refine statistics of one step: visible (radii > 0) Gaussians accumulate |dL/dmean2D| (NDC-scaled, as returned in
+ * TgsGrads.dmeans2D), a visit count and their maximum screen radius */
+int tgs_densify_stats(int32_t N, const float* dmeans2D, const int32_t* radii, float* grad_accum,
+                      int32_t* vis_count, int32_t* max_radii, void* stream);
+
+typedef struct TgsDensifyConfig {
+    float grad_thresh;        /* mean |dL/dmean2D| above which a Gaussian is duplicated / split (0.0002) */
+    float size_thresh;        /* max world scale above which it is split instead of duplicated (0.01) */
+    float cull_alpha_thresh;  /* cull when sigmoid(opacity) < this (0.1) */
+    float cull_scale_thresh;  /* cull when max world scale > this (0.5) */
+    float split_shrink;       /* split samples get scale / this (1.6) */
+    int32_t n_split_samples;  /* 2 */
+} TgsDensifyConfig;
+typedef struct TgsParamSet { float* means; float* shs; float* opacity; float* scales; float* quats; } TgsParamSet;
+size_t tgs_densify_temp_bytes(int32_t N);
+/* counts[i] (bit 31 = split) / offsets[i] (exclusive scan) of the outputs of Gaussian i: culled 0, kept 1,
+ * duplicated 2 (itself, copy), split n_split_samples (the original is dropped).  Synchronises to return the total. */
+int tgs_densify_plan(int32_t N, const float* opacity_logit, const float* scales_log, const float* grad_accum,
+                     const int32_t* vis_count, const TgsDensifyConfig* cfg, int32_t allow_split_dup,
+                     uint32_t* counts, uint32_t* offsets, void* temp, size_t temp_bytes,
+                     int64_t* total_host, void* stream);
+/* in_pmv / out_pmv: 3 TgsParamSet each = (values, exp_avg, exp_avg_sq); raw parameters (opacity logit [N],
+ * scales log [N,3], quats [N,4], shs [N,K,3], means [N,3]).  noise: [N, n_split_samples, 3] ~ N(0,1).
+ * src_out[o] = source id for carried-over entries, -(source id + 1) for new ones (zero Adam moments). */
+int tgs_densify_apply(int32_t N, int32_t K, const uint32_t* counts, const uint32_t* offsets, const float* noise,
+                      const TgsDensifyConfig* cfg, const TgsParamSet* in_pmv, const TgsParamSet* out_pmv,
+                      int32_t* src_out, void* stream);
 
 #ifdef __cplusplus
 }

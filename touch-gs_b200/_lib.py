@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TGS_LIB_PATH") or os.path.join(HERE, "libtgs.so")   # override: A/B builds
 
-TGS_ABI_VERSION = 1
+TGS_ABI_VERSION = 2
 BUF_GEOM, BUF_BINNING, BUF_IMAGE, BUF_TEMP = 0, 1, 2, 3
 LOSS_NONE, LOSS_L1, LOSS_L2 = 0, 1, 2
 LOSS_MODES = {"none": LOSS_NONE, "l1": LOSS_L1, "l2": LOSS_L2}
@@ -41,7 +41,8 @@ class TgsGaussians(C.Structure):
 
 
 class TgsTouch(C.Structure):
-    _fields_ = [("target", c_fp), ("weight", c_fp), ("scale", c_fp), ("mode", C.c_int32)]
+    _fields_ = [("target", c_fp), ("weight", c_fp), ("scale", c_fp), ("mode", C.c_int32),
+                ("row_begin", C.c_int32), ("row_end", C.c_int32)]
 
 
 class TgsSaved(C.Structure):
@@ -78,6 +79,22 @@ class TgsRefBinningLayout(C.Structure):
                  "temp_bytes", "total")]
 
 
+class TgsAdamGroup(C.Structure):
+    _fields_ = [("param", c_fp), ("grad", c_fp), ("exp_avg", c_fp), ("exp_avg_sq", c_fp), ("numel", C.c_int64),
+                ("lr", C.c_float), ("lr_tail", C.c_float), ("period", C.c_int32), ("head", C.c_int32)]
+
+
+class TgsDensifyConfig(C.Structure):
+    _fields_ = [("grad_thresh", C.c_float), ("size_thresh", C.c_float), ("cull_alpha_thresh", C.c_float),
+                ("cull_scale_thresh", C.c_float), ("split_shrink", C.c_float), ("n_split_samples", C.c_int32)]
+
+
+class TgsParamSet(C.Structure):
+    _fields_ = [("means", c_fp), ("shs", c_fp), ("opacity", c_fp), ("scales", c_fp), ("quats", c_fp)]
+
+
+ADAM_MAX_GROUPS = 8
+
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int, C.c_size_t)
 
 # every symbol include/tgs.h declares: (restype, argtypes)
@@ -105,6 +122,20 @@ SIGNATURES = {
     "tgs_geom_layout": (C.c_int, [C.c_int32, C.POINTER(TgsGeomLayout)]),
     "tgs_binning_layout": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(TgsBinningLayout)]),
     "tgs_image_layout": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(TgsImageLayout)]),
+    "tgs_photometric_scratch_floats": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "tgs_photometric_loss_forward": (C.c_int, [c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                               c_fp, c_fp, c_fp, c_fp]),
+    "tgs_photometric_loss_backward": (C.c_int, [c_fp, c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                                C.c_int32, C.c_int32, C.c_float, c_fp, c_fp, c_fp]),
+    "tgs_activate_forward": (C.c_int, [C.c_int32, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "tgs_activate_backward": (C.c_int, [C.c_int32, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "tgs_adam_step": (C.c_int, [C.POINTER(TgsAdamGroup), C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, c_fp]),
+    "tgs_densify_stats": (C.c_int, [C.c_int32, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "tgs_densify_temp_bytes": (C.c_size_t, [C.c_int32]),
+    "tgs_densify_plan": (C.c_int, [C.c_int32, c_fp, c_fp, c_fp, c_fp, C.POINTER(TgsDensifyConfig), C.c_int32,
+                                   c_fp, c_fp, c_fp, C.c_size_t, C.POINTER(C.c_int64), c_fp]),
+    "tgs_densify_apply": (C.c_int, [C.c_int32, C.c_int32, c_fp, c_fp, c_fp, C.POINTER(TgsDensifyConfig),
+                                    C.POINTER(TgsParamSet), C.POINTER(TgsParamSet), c_fp, c_fp]),
     "tgs_refstructure_binning_layout": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.POINTER(TgsRefBinningLayout)]),
     "tgs_refstructure_forward": (C.c_int, [C.POINTER(TgsSettings), C.POINTER(TgsGaussians), ALLOC_FN, C.c_void_p,
                                            c_fp, c_fp, c_fp, c_fp, C.POINTER(TgsSaved), c_fp]),

@@ -26,6 +26,7 @@ UNITS = {
     "binning.cu": [],
     "render.cu": [],
     "refstructure.cu": [],
+    "train_ops.cu": [],
     "api.cu": [],
     "host_step.cu": [],
     "touch_inputs.cu": ["--fmad=false"],

@@ -255,7 +255,7 @@ k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
              const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
              const float* __restrict__ dL_dalpha, const float* __restrict__ t_target,
              const float* __restrict__ t_weight, const float* __restrict__ t_scale, int t_mode,
-             float* __restrict__ residual, float* __restrict__ sgrad) {
+             int t_row0, int t_row1, float* __restrict__ residual, float* __restrict__ sgrad) {
     __shared__ __align__(128) float4 sbuf[2][kBwdBatch * 3];
     __shared__ __align__(8) uint64_t full[2];
     const int lane = threadIdx.x;
@@ -293,7 +293,7 @@ k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
             float gDhat = dL_ddepth ? dL_ddepth[pix] : 0.0f;
             float gA = dL_dalpha ? dL_dalpha[pix] : 0.0f;
             float res = 0.0f;
-            if (t_target != nullptr && A > 0.0f) {
+            if (t_target != nullptr && A > 0.0f && py >= t_row0 && py < t_row1) {
                 const float tgt = t_target[pix];
                 if (tgt > 0.0f) {
                     const float dhat = normalize ? D / A : D;
@@ -455,14 +455,16 @@ int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, BinView bv, I
     int nt = cam.Tx * (cam.row1 - cam.row0);
     if (nt <= 0) return 0;
     const float* tt = nullptr; const float* tw = nullptr; const float* ts = nullptr; int mode = TGS_LOSS_NONE;
+    int tr0 = 0, tr1 = cam.H;
     if (touch && touch->target) {
         tt = touch->target; tw = touch->weight; ts = touch->scale; mode = touch->mode;
+        if (touch->row_end > touch->row_begin) { tr0 = touch->row_begin; tr1 = touch->row_end; }
         if (mode != TGS_LOSS_NONE && ts == nullptr) { tgs_set_error("touch loss enabled but scale pointer is NULL"); return TGS_EINVAL; }
     }
     TgsProfScope prof(TGS_STAGE_RENDER_BWD, st);
     k_render_bwd<<<2 * nt, kBwdThreads, 0, st>>>(bv.ranges, bv.records, cam.W, cam.H, cam.Tx, cam.row0, s->bg,
                                      s->depth_normalize, iv.final_T, iv.n_contrib, iv.depth_raw, dL_dcolor,
-                                     dL_ddepth, dL_dalpha, tt, tw, ts, mode, residual, screen_grads);
+                                     dL_ddepth, dL_dalpha, tt, tw, ts, mode, tr0, tr1, residual, screen_grads);
     tgs_count_own(1);
     TGS_KERNEL_CHECK(st, s->debug);
     return 0;

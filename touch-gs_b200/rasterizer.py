@@ -56,6 +56,7 @@ class TouchOptions(NamedTuple):
     process_group: object = None                   # all-reduce group for the screen-space gradients
     rendered_hint: int = 0                         # > 0: speculative sizing (hides the forward's host sync)
     info: Optional[dict] = None                    # filled with num_rendered / capacity of the call
+    touch_rows: Optional[Tuple[int, int]] = None   # pixel rows where the touch loss applies (None = all rows)
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -253,7 +254,9 @@ class _RasterizeGaussians(torch.autograd.Function):
                 keep.append(scale)
                 touch = L.TgsTouch(target=touch_depth.data_ptr(),
                                    weight=None if touch_weight is None else touch_weight.data_ptr(),
-                                   scale=scale.data_ptr(), mode=L.LOSS_MODES[opt.depth_loss])
+                                   scale=scale.data_ptr(), mode=L.LOSS_MODES[opt.depth_loss],
+                                   row_begin=0 if opt.touch_rows is None else int(opt.touch_rows[0]),
+                                   row_end=0 if opt.touch_rows is None else int(opt.touch_rows[1]))
             sgrad = torch.empty((max(N, 1), L.NGRAD), dtype=torch.float32, device=dev)
             L.check(lib.tgs_backward_render(C.byref(s), C.byref(g), C.byref(saved), _ptr(g_color), _ptr(g_depth),
                                             _ptr(g_alpha), None if touch is None else C.byref(touch), None,
@@ -319,7 +322,7 @@ class GaussianRasterizer(torch.nn.Module):
                 rotations=None, cov3D_precomp=None, *, touch_depth=None, touch_weight=None,
                 depth_loss: str = "none", depth_loss_mult: float = 1.0, depth_normalize: bool = True,
                 depth_loss_norm: Optional[float] = None, tile_rows=None, process_group=None,
-                rendered_hint: int = 0):
+                rendered_hint: int = 0, touch_rows=None):
         if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
             raise Exception("Please provide excatly one of either SHs or precomputed colors!")
         if ((scales is None or rotations is None) and cov3D_precomp is None) or \
@@ -328,7 +331,7 @@ class GaussianRasterizer(torch.nn.Module):
         e = torch.Tensor([]).to(means3D.device)
         info = {}
         opt = TouchOptions(touch_depth, touch_weight, depth_loss, depth_loss_mult, depth_normalize,
-                           depth_loss_norm, tile_rows, process_group, rendered_hint, info)
+                           depth_loss_norm, tile_rows, process_group, rendered_hint, info, touch_rows)
         out = rasterize_gaussians(means3D, means2D,
                                   e if shs is None else shs, e if colors_precomp is None else colors_precomp,
                                   opacities, e if scales is None else scales, e if rotations is None else rotations,
