@@ -46,8 +46,11 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-refcuda", action="store_true", help="skip the reference-structure CUDA comparison arm")
     ap.add_argument("--cameras", type=int, default=8)
-    ap.add_argument("--workload", default="rasterizer", choices=["rasterizer", "touch_inputs"],
-                    help="touch_inputs: roofline of the per-pixel touch/vision fusion kernel (SURVEY §8f N2), not the headline metric")
+    ap.add_argument("--workload", default="rasterizer", choices=["rasterizer", "touch_inputs", "train_step"],
+                    help="touch_inputs: roofline of the per-pixel touch/vision fusion kernel (SURVEY §8f N2); train_step: the "
+                         "full Touch-GS train step (activations, rasterizer, L1+SSIM loss, fused touch depth-L1, Adam, refine "
+                         "every --refine-every steps: SURVEY §8f N1 / BASELINE config c5); neither is the headline metric")
+    ap.add_argument("--refine-every", type=int, default=100)
     ap.add_argument("--no-hints", action="store_true", help="synchronous sizing in every forward (no rendered_hint)")
     return ap.parse_args()
 
@@ -254,6 +257,33 @@ class Stepper:
         return int(sum(v.numel() * v.element_size() for v in b["host"].values()))
 
 
+class TrainStepper(Stepper):
+    """One FULL train step through the public trainer API (TouchGSTrainer.train_step): activations -> rasterizer
+    forward -> L1 + SSIM photometric loss -> backward with the fused touch depth-L1 gradient -> [all-reduce] ->
+    activation backward -> refine statistics -> one-launch Adam; refine (densify / cull) every `refine_every` steps."""
+
+    def __init__(self, cfg, params, bg, dev, band, group, refine_every):
+        super().__init__(cfg, params, bg, dev, band, group)
+        T = self.T
+        raw = [params["means3D"].detach(), params["shs"].detach(),
+               torch.logit(params["opacities"].detach().reshape(-1).clamp(1e-4, 1 - 1e-4)),
+               torch.log(params["scales"].detach()), params["rotations"].detach()]
+        tc = T.TrainConfig(sh_degree=cfg["sh_degree"], depth_loss_mult=DEPTH_LOSS_MULT,
+                           depth_loss_type="DEPTH_UNCERTAINTY_WEIGHTED_LOSS", uncertainty_weight=1.0,
+                           refine_every=refine_every, warmup_length=0)
+        self.trainer = T.TouchGSTrainer(*raw, tc, process_group=group)
+        self.n_history = [self.trainer.num_points]
+
+    def _run(self, cam, view, proj, campos, gt, target, weight):
+        T, cfg = self.T, self.cfg
+        rs = T.GaussianRasterizationSettings(cfg["H"], cfg["W"], cam.tanfovx, cam.tanfovy, self.bg, 1.0, view, proj,
+                                             cfg["sh_degree"], campos, False, False)
+        loss = self.trainer.train_step(rs, gt, target, weight, view_key=id(cam) if self.use_hints else None)
+        if self.trainer.num_points != self.n_history[-1]:
+            self.n_history.append(self.trainer.num_points)
+        return loss
+
+
 # ------------------------------------------------------------------------ CPU reference
 class CpuReference:
     """The reference's CPU path for this hot path: the pure-PyTorch oracle (kind = "port"; the reference
@@ -421,7 +451,13 @@ def main():
     band = None if world == 1 else T.sharding.even_bands(H, world)[rank]
 
     scene, params, batches, bg = make_workload(cfg, N, args.cameras, dev, rank, band)
-    stepper = Stepper(cfg, params, bg, dev, band, group)
+    train_mode = args.workload == "train_step"
+    if train_mode:
+        stepper = TrainStepper(cfg, params, bg, dev, band, group, args.refine_every)
+        args.no_refcuda = True
+        args.no_cpu_baseline = True
+    else:
+        stepper = Stepper(cfg, params, bg, dev, band, group)
     stepper.use_hints = not args.no_hints
     # allocator priming (setup, not warm-up): every camera has its own instance count, so touch each
     # once so that torch's caching allocator owns blocks of every size before anything is timed
@@ -537,14 +573,19 @@ def main():
     # ---- roofline of the dominant kernel, from the stage timers of the timed region
     peak, peak_src = peaks()
     stage_ms = {k: (v[0] / max(v[1], 1), v[1]) for k, v in prof.items()}
-    dom = max(("render_fwd", "render_bwd", "sort", "preprocess", "preprocess_bwd", "pack", "duplicate"),
-              key=lambda k: prof[k][0])
+    cands = ("render_fwd", "render_bwd", "sort", "preprocess", "preprocess_bwd", "pack", "duplicate")
+    if train_mode:
+        cands += ("adam", "photo_fwd", "photo_bwd")
+    dom = max(cands, key=lambda k: prof[k][0])
     P_band = W * (stepper.y1 - stepper.y0)
     per_launch_bytes = {
         "render_bwd": 84 * I_cam0 + 32 * P_band,          # id 4 + record 40 + grad accumulate 40 per instance; 32 B / pixel
         "render_fwd": 44 * I_cam0 + 24 * P_band,          # id 4 + record 40 per instance; 24 B / pixel written
         "sort": 24 * I_cam0, "pack": 8 * I_cam0 + 96 * I_cam0, "duplicate": 20 * N + 12 * I_cam0,
         "preprocess": N * (4 * (11 + 3 * K) + 48 + 8), "preprocess_bwd": N * (4 * (11 + 3 * K) * 2 + 48),
+        # train step: Adam reads p,g,m,v and writes p,m,v = 28 B per parameter element; the loss kernels
+        # read the two images (24 B/px) and write / read the 3 derivative maps (36 B/px) and write the gradient (12 B/px)
+        "adam": 28 * N * (11 + 3 * K), "photo_fwd": 60 * P_band, "photo_bwd": 72 * P_band,
     }[dom]
     dom_ms = stage_ms[dom][0]
     traffic = None          # DRAM bytes of the dominant kernel from the committed ncu capture (c3, camera 0)
@@ -558,7 +599,8 @@ def main():
     T_band = Tx * (Ty if band is None else band[1] - band[0])
     step_bytes = alg_bytes(N, I_cam0, P_band, T_band, K)
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "metric": METRIC if not train_mode else "full train step Gaussians/sec (BASELINE config c5 pipeline: rasterizer fwd+bwd + L1/SSIM + fused touch depth-L1 + Adam + refine)",
+        "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.config}: {N} Gaussians, {W}x{H}, SH deg {cfg['sh_degree']}, fused touch depth-L1 "
@@ -577,6 +619,13 @@ def main():
         "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved_GBps": step_bytes / (ms / steps * 1e-3) / 1e9,
                           "frac": step_bytes / (ms / steps * 1e-3) / 1e9 / peak},
     }
+    if train_mode:
+        out["config"]["workload"] = (f"train_step on {args.config}: {N} Gaussians initially, {W}x{H}, SH deg {cfg['sh_degree']}, "
+                                     f"L1+SSIM (lambda 0.2) + fused touch depth-L1 (uncertainty-weighted, mult {DEPTH_LOSS_MULT}), "
+                                     f"Adam over 5 tensors in one launch, refine every {args.refine_every} steps, "
+                                     f"{len(batches)} orbit cameras cycled; value = initial N x steps / time")
+        out["config"]["population_history"] = stepper.n_history
+        out["config"]["num_rendered_cam0"] = I_cam0
     if e2e is not None:
         out["e2e"] = e2e
     if refcuda is not None:

@@ -139,7 +139,12 @@ void        tgs_launch_counts(uint64_t* own, uint64_t* cub);
 #define TGS_STAGE_LOSS_SCALE      6
 #define TGS_STAGE_RENDER_BWD      7
 #define TGS_STAGE_PREPROCESS_BWD  8
-#define TGS_NUM_STAGES            9
+#define TGS_STAGE_PHOTO_FWD       9   /* train step: fused L1+SSIM loss forward */
+#define TGS_STAGE_PHOTO_BWD       10
+#define TGS_STAGE_ACTIVATE        11  /* activations forward + backward */
+#define TGS_STAGE_ADAM            12
+#define TGS_STAGE_REFINE          13  /* refine statistics + densify plan / apply */
+#define TGS_NUM_STAGES            14
 int tgs_profile_enable(int32_t on);
 int tgs_profile_read(float* ms_per_stage, int32_t* launches_per_stage);
 
@@ -340,8 +345,8 @@ typedef struct TgsAdamGroup {
     float lr, lr_tail;
     int32_t period, head;
 } TgsAdamGroup;
-int tgs_adam_step(const TgsAdamGroup* groups_host, int32_t n_groups, int32_t step, float beta1, float beta2,
-                  float eps, void* stream);
+int tgs_adam_step(const TgsAdamGroup* groups_host, int32_t n_groups, int32_t step, double beta1, double beta2,
+                  double eps, void* stream);   /* doubles: 1-beta and the bias corrections are formed in double, as torch does */
 
 /* refine statistics of one step: visible (radii > 0) Gaussians accumulate |dL/dmean2D| (NDC-scaled, as returned in
  * TgsGrads.dmeans2D), a visit count and their maximum screen radius */

@@ -129,7 +129,7 @@ SIGNATURES = {
                                                 C.c_int32, C.c_int32, C.c_float, c_fp, c_fp, c_fp]),
     "tgs_activate_forward": (C.c_int, [C.c_int32, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "tgs_activate_backward": (C.c_int, [C.c_int32, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
-    "tgs_adam_step": (C.c_int, [C.POINTER(TgsAdamGroup), C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, c_fp]),
+    "tgs_adam_step": (C.c_int, [C.POINTER(TgsAdamGroup), C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, c_fp]),
     "tgs_densify_stats": (C.c_int, [C.c_int32, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "tgs_densify_temp_bytes": (C.c_size_t, [C.c_int32]),
     "tgs_densify_plan": (C.c_int, [C.c_int32, c_fp, c_fp, c_fp, c_fp, C.POINTER(TgsDensifyConfig), C.c_int32,
@@ -179,7 +179,7 @@ def check(rc: int, what: str) -> None:
 
 
 STAGES = ("preprocess", "scan", "duplicate", "sort", "pack", "render_fwd", "loss_scale", "render_bwd",
-          "preprocess_bwd")
+          "preprocess_bwd", "photo_fwd", "photo_bwd", "activate", "adam", "refine")
 
 
 def profile_enable(on: bool) -> None:

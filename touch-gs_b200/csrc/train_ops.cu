@@ -206,12 +206,13 @@ struct AdamArgs {
     float step_size[TGS_ADAM_MAX_GROUPS], step_size_tail[TGS_ADAM_MAX_GROUPS];
     int n;
     float beta1, beta2, eps, inv_bc2_sqrt;
+    float omb1, omb2;               // 1-beta1, 1-beta2 formed in DOUBLE on the host (as torch does), then rounded
 };
 
-__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float step, float b1, float b2, float eps,
-                                         float inv_bc2) {
-    m = m + (g - m) * (1.0f - b1);                // lerp(m, g, 1-b1)
-    v = v * b2 + ((1.0f - b2) * g) * g;           // mul_(b2).addcmul_(g, g, 1-b2)
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float step, const AdamArgs& a) {
+    const float eps = a.eps, inv_bc2 = a.inv_bc2_sqrt;
+    m = m + (g - m) * a.omb1;                     // lerp(m, g, 1-b1)
+    v = v * a.beta2 + (a.omb2 * g) * g;           // mul_(b2).addcmul_(g, g, 1-b2)
     const float denom = sqrtf(v) * inv_bc2 + eps;
     p = p - step * (m / denom);                   // addcdiv_(m, denom, -step)
 }
@@ -237,10 +238,10 @@ k_adam(const __grid_constant__ AdamArgs a) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) { int rr = r + k; if (rr >= G.period) rr -= G.period; st[k] = rr < G.head ? s0 : s1; }
         }
-        adam_one(p.x, g.x, m.x, v.x, st[0], a.beta1, a.beta2, a.eps, a.inv_bc2_sqrt);
-        adam_one(p.y, g.y, m.y, v.y, st[1], a.beta1, a.beta2, a.eps, a.inv_bc2_sqrt);
-        adam_one(p.z, g.z, m.z, v.z, st[2], a.beta1, a.beta2, a.eps, a.inv_bc2_sqrt);
-        adam_one(p.w, g.w, m.w, v.w, st[3], a.beta1, a.beta2, a.eps, a.inv_bc2_sqrt);
+        adam_one(p.x, g.x, m.x, v.x, st[0], a);
+        adam_one(p.y, g.y, m.y, v.y, st[1], a);
+        adam_one(p.z, g.z, m.z, v.z, st[2], a);
+        adam_one(p.w, g.w, m.w, v.w, st[3], a);
         p4[i] = p; m4[i] = m; v4[i] = v;
     }
     if (blockIdx.x == 0 && threadIdx.x < (G.numel & 3)) {          // scalar tail
@@ -248,7 +249,7 @@ k_adam(const __grid_constant__ AdamArgs a) {
         float st = s0;
         if (two) st = (int)(i % G.period) < G.head ? s0 : s1;
         float p = G.param[i], m = G.exp_avg[i], v = G.exp_avg_sq[i];
-        adam_one(p, G.grad[i], m, v, st, a.beta1, a.beta2, a.eps, a.inv_bc2_sqrt);
+        adam_one(p, G.grad[i], m, v, st, a);
         G.param[i] = p; G.exp_avg[i] = m; G.exp_avg_sq[i] = v;
     }
 }
@@ -359,6 +360,7 @@ extern "C" int tgs_photometric_loss_forward(const float* color, const float* gt,
     if (row_begin < 0 || row_end > H) { tgs_set_error("tgs_photometric_loss_forward: rows outside the image"); return TGS_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
     static const SsimTaps taps = make_taps();
+    TgsProfScope prof(TGS_STAGE_PHOTO_FWD, st);
     TGS_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(double), st));
     dim3 grid((W + kST - 1) / kST, (row_end - row_begin + kST - 1) / kST, 3);
     k_ssim_fwd<<<grid, 256, 0, st>>>(color, gt, W, H, row_begin, row_end, taps, dmaps, sums);
@@ -378,6 +380,7 @@ extern "C" int tgs_photometric_loss_backward(const float* color, const float* gt
     cudaStream_t st = (cudaStream_t)stream;
     static const SsimTaps taps = make_taps();
     dim3 grid((W + kST - 1) / kST, (out_row_end - out_row_begin + kST - 1) / kST, 3);
+    TgsProfScope prof(TGS_STAGE_PHOTO_BWD, st);
     k_ssim_bwd<<<grid, 256, 0, st>>>(color, gt, dmaps, W, H, row_begin, row_end, out_row_begin, out_row_end, taps,
                                      lambda_dssim, (float)(1.0 / (3.0 * W * (double)H)), grad_out, dL_dcolor);
     tgs_count_own(1);
@@ -390,6 +393,7 @@ extern "C" int tgs_activate_forward(int32_t N, const float* scales_log, const fl
     if (N < 0 || (N > 0 && (!scales_log || !quats || !opacity_logit || !scales || !rotations || !opacities))) {
         tgs_set_error("tgs_activate_forward: bad arguments"); return TGS_EINVAL; }
     if (N == 0) return 0;
+    TgsProfScope prof(TGS_STAGE_ACTIVATE, (cudaStream_t)stream);
     k_activate_fwd<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(N, scales_log, quats, opacity_logit, scales, rotations, opacities);
     tgs_count_own(1);
     TGS_CUDA(cudaGetLastError());
@@ -403,6 +407,7 @@ extern "C" int tgs_activate_backward(int32_t N, const float* scales_log, const f
                             !dscales_log || !dquats || !dopacity_logit))) {
         tgs_set_error("tgs_activate_backward: bad arguments"); return TGS_EINVAL; }
     if (N == 0) return 0;
+    TgsProfScope prof(TGS_STAGE_ACTIVATE, (cudaStream_t)stream);
     k_activate_bwd<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(N, scales_log, quats, opacity_logit, dscales, drotations,
                                                                        dopacities, dscales_log, dquats, dopacity_logit);
     tgs_count_own(1);
@@ -410,13 +415,14 @@ extern "C" int tgs_activate_backward(int32_t N, const float* scales_log, const f
     return 0;
 }
 
-extern "C" int tgs_adam_step(const TgsAdamGroup* groups, int32_t n_groups, int32_t step, float beta1, float beta2,
-                             float eps, void* stream) {
+extern "C" int tgs_adam_step(const TgsAdamGroup* groups, int32_t n_groups, int32_t step, double beta1, double beta2,
+                             double eps, void* stream) {
     if (!groups || n_groups <= 0 || n_groups > TGS_ADAM_MAX_GROUPS || step <= 0) { tgs_set_error("tgs_adam_step: bad arguments"); return TGS_EINVAL; }
     AdamArgs a;
-    a.n = n_groups; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
-    const double bc1 = 1.0 - std::pow((double)beta1, (double)step);
-    const double bc2 = 1.0 - std::pow((double)beta2, (double)step);
+    a.n = n_groups; a.beta1 = (float)beta1; a.beta2 = (float)beta2; a.eps = (float)eps;
+    a.omb1 = (float)(1.0 - beta1); a.omb2 = (float)(1.0 - beta2);
+    const double bc1 = 1.0 - std::pow(beta1, (double)step);
+    const double bc2 = 1.0 - std::pow(beta2, (double)step);
     a.inv_bc2_sqrt = (float)(1.0 / std::sqrt(bc2));
     int64_t most = 0;
     for (int i = 0; i < n_groups; ++i) {
@@ -433,6 +439,7 @@ extern "C" int tgs_adam_step(const TgsAdamGroup* groups, int32_t n_groups, int32
     int64_t blocks = ((most >> 2) + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;                  // persistent-style grid: 8 CTAs per SM per group
     if (blocks < 1) blocks = 1;
+    TgsProfScope prof(TGS_STAGE_ADAM, (cudaStream_t)stream);
     k_adam<<<dim3((unsigned)blocks, n_groups), 256, 0, (cudaStream_t)stream>>>(a);
     tgs_count_own(1);
     TGS_CUDA(cudaGetLastError());
@@ -443,6 +450,7 @@ extern "C" int tgs_densify_stats(int32_t N, const float* dmeans2D, const int32_t
                                  int32_t* vis_count, int32_t* max_radii, void* stream) {
     if (N < 0 || (N > 0 && (!dmeans2D || !radii || !grad_accum || !vis_count || !max_radii))) { tgs_set_error("tgs_densify_stats: bad arguments"); return TGS_EINVAL; }
     if (N == 0) return 0;
+    TgsProfScope prof(TGS_STAGE_REFINE, (cudaStream_t)stream);
     k_densify_stats<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(N, dmeans2D, radii, grad_accum, vis_count, max_radii);
     tgs_count_own(1);
     TGS_CUDA(cudaGetLastError());
@@ -464,6 +472,7 @@ extern "C" int tgs_densify_plan(int32_t N, const float* opacity_logit, const flo
         tgs_set_error("tgs_densify_plan: bad arguments"); return TGS_EINVAL; }
     if (cfg->n_split_samples < 1 || cfg->n_split_samples > 8) { tgs_set_error("tgs_densify_plan: n_split_samples out of range"); return TGS_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
+    TgsProfScope prof(TGS_STAGE_REFINE, st);
     k_densify_classify<<<(N + 255) / 256, 256, 0, st>>>(N, opacity_logit, scales_log, grad_accum, vis_count, *cfg,
                                                         allow_split_dup, counts);
     tgs_count_own(1);
@@ -487,6 +496,7 @@ extern "C" int tgs_densify_apply(int32_t N, int32_t K, const uint32_t* counts, c
     const TgsParamSet& p = in_pmv[0]; const TgsParamSet& o = out_pmv[0];
     if (!p.means || !p.scales || !p.quats || !o.means || !o.scales || !o.quats || !noise) { tgs_set_error("tgs_densify_apply: means / scales / quats / noise required"); return TGS_EINVAL; }
     const int64_t threads = (int64_t)N * 32;
+    TgsProfScope prof(TGS_STAGE_REFINE, (cudaStream_t)stream);
     k_densify_apply<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         N, K, counts, offsets, noise, *cfg, in_pmv[0], in_pmv[1], in_pmv[2], out_pmv[0], out_pmv[1], out_pmv[2], src_out);
     tgs_count_own(1);
