@@ -76,35 +76,62 @@ def _chk(t: Optional[torch.Tensor], name: str, shape, device, dtype=torch.float3
     return t.contiguous()
 
 
-class _Scratch:
-    """Allocator handed to the C ABI: the three saved byte buffers are torch tensors, so they come
-    from torch's caching allocator on the caller's device and are kept alive by ``ctx``.
+import threading
 
-    The ctypes callback closes over a plain dict, never over ``self``: a bound-method callback would
-    form a reference cycle that keeps ~1 GB of scratch per call alive until the cyclic GC runs."""
+_tls = threading.local()
 
-    def __init__(self, device):
-        bufs, err = {}, []
 
-        def _alloc(_user, which, nbytes, _device=device, _bufs=bufs, _err=err):
+def _thread_alloc():
+    """ONE ctypes callback per thread (building a CFUNCTYPE object per call costs ~10 us).  The callback writes into
+    the thread-local `state` dict that `_Scratch` re-arms for every call; it never references a `_Scratch` instance,
+    so no reference cycle can keep ~1 GB of scratch per call alive until the cyclic GC runs."""
+    cb = getattr(_tls, "cb", None)
+    if cb is None:
+        state = {"bufs": None, "err": None, "device": None}
+
+        def _alloc(_user, which, nbytes, _state=state):
             try:
-                t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=_device)
-                _bufs[int(which)] = t
+                t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=_state["device"])
+                _state["bufs"][int(which)] = t
                 return t.data_ptr()
             except Exception as e:  # noqa: BLE001 - must not propagate through the C frame
-                _err.append(e)
+                _state["err"] = e
                 return None
 
-        self.bufs, self._err = bufs, err
-        self.cb = L.ALLOC_FN(_alloc)
+        _tls.state, _tls.cb = state, L.ALLOC_FN(_alloc)
+        cb = _tls.cb
+    return cb, _tls.state
+
+
+class _Scratch:
+    """Allocator handed to the C ABI: the three saved byte buffers are torch tensors, so they come from torch's
+    caching allocator on the caller's device and are kept alive by ``ctx``."""
+
+    def __init__(self, device):
+        self.cb, self._state = _thread_alloc()
+        self.bufs = {}
+        self._state["bufs"], self._state["err"], self._state["device"] = self.bufs, None, device
 
     @property
     def error(self):
-        return self._err[0] if self._err else None
+        return self._state["err"]
+
+    def disarm(self):
+        """Drop the callback's reference to this call's buffers (they now belong to ``self.bufs`` / ``ctx`` only)."""
+        if self._state["bufs"] is self.bufs:
+            self._state["bufs"] = None
+
+    def __del__(self):
+        self.disarm()
 
 
 def _stream_ptr(device):
-    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    """Raw cudaStream_t of torch's current stream on `device` (the C accessor: several times cheaper than building a
+    torch.cuda.Stream object; this is called for every C-ABI entry point of every step)."""
+    idx = device.index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(idx))
 
 
 def _make_settings(rs: GaussianRasterizationSettings, opt: TouchOptions, K: int, keep):
@@ -137,6 +164,18 @@ def _make_gaussians(means3D, opacities, sh, colors, scales, rots, cov3D):
         scales=None if scales is None else scales.data_ptr(),
         rotations=None if rots is None else rots.data_ptr(),
         cov3D_precomp=None if cov3D is None else cov3D.data_ptr())
+
+
+_EMPTY = {}
+
+
+def _empty_on(device):
+    """Cached zero-element placeholder for absent optional tensors (the reference-era module builds a CPU tensor and
+    copies it to the device on every call)."""
+    t = _EMPTY.get(device)
+    if t is None:
+        t = _EMPTY[device] = torch.empty(0, device=device)
+    return t
 
 
 def _empty_if(t):
@@ -197,11 +236,13 @@ class _RasterizeGaussians(torch.autograd.Function):
             rc = lib.tgs_forward(C.byref(s), C.byref(g), scratch.cb, None, _ptr(color), _ptr(depth), _ptr(alpha),
                                  _ptr(radii), _ptr(touch_depth), _ptr(resid) if touch_depth is not None else None,
                                  C.byref(saved), _stream_ptr(dev))
+            scratch.disarm()
             if scratch.error is not None:
                 raise scratch.error
             L.check(rc, "tgs_forward")
 
         ctx.rs, ctx.opt, ctx.K = rs, opt, K
+        ctx.settings, ctx.keep = s, keep           # the validated C structs are reused by backward
         ctx.opacity_shape = opacity_shape
         ctx.num_rendered = int(saved.num_rendered)
         ctx.capacity = int(saved.capacity)
@@ -210,7 +251,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             opt.info["capacity"] = ctx.capacity
         ctx.has = (sh is not None, colors_precomp is not None, scales is not None, cov3Ds_precomp is not None)
         ctx.touch = (touch_depth, touch_weight)
-        none = torch.empty(0, device=dev)
+        none = _empty_on(dev)
         ctx.save_for_backward(means3D, opacities, sh if sh is not None else none,
                               colors_precomp if colors_precomp is not None else none,
                               scales if scales is not None else none,
@@ -234,9 +275,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         dev = means3D.device
         N = int(means3D.shape[0])
         H, W = int(rs.image_height), int(rs.image_width)
-        keep = []
+        keep = ctx.keep
         with torch.cuda.device(dev):
-            s, _ = _make_settings(rs, opt, K, keep)
+            s = ctx.settings
             g = _make_gaussians(means3D, opacities, sh, colors, scales, rots, cov3D)
             saved = L.TgsSaved(geom=geom.data_ptr(), binning=binning.data_ptr(), image=image.data_ptr(),
                                num_rendered=ctx.num_rendered, capacity=ctx.capacity)
@@ -328,7 +369,7 @@ class GaussianRasterizer(torch.nn.Module):
         if ((scales is None or rotations is None) and cov3D_precomp is None) or \
                 ((scales is not None or rotations is not None) and cov3D_precomp is not None):
             raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
-        e = torch.Tensor([]).to(means3D.device)
+        e = _empty_on(means3D.device)
         info = {}
         opt = TouchOptions(touch_depth, touch_weight, depth_loss, depth_loss_mult, depth_normalize,
                            depth_loss_norm, tile_rows, process_group, rendered_hint, info, touch_rows)

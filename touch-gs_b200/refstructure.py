@@ -50,6 +50,7 @@ class _RefStructureRasterize(torch.autograd.Function):
             saved = L.TgsSaved()
             rc = lib.tgs_refstructure_forward(C.byref(s), C.byref(g), scratch.cb, None, _ptr(color), _ptr(depth),
                                               _ptr(alpha), _ptr(radii), C.byref(saved), _stream_ptr(dev))
+            scratch.disarm()
             if scratch.error is not None:
                 raise scratch.error
             L.check(rc, "tgs_refstructure_forward")
