@@ -51,6 +51,9 @@ def parse():
                          "full Touch-GS train step (activations, rasterizer, L1+SSIM loss, fused touch depth-L1, Adam, refine "
                          "every --refine-every steps: SURVEY §8f N1 / BASELINE config c5); neither is the headline metric")
     ap.add_argument("--refine-every", type=int, default=100)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU exchange of the [N,10] screen gradients: p2p = gather fused into the preprocess-backward "
+                         "kernel over peer-mapped memory (NVLink); nccl = one all-reduce (also the fallback if p2p is unavailable)")
     ap.add_argument("--no-hints", action="store_true", help="synchronous sizing in every forward (no rendered_hint)")
     return ap.parse_args()
 
@@ -172,6 +175,7 @@ class Stepper:
         import touchgs_b200 as T
         self.T, self.cfg, self.p, self.bg, self.dev = T, cfg, params, bg, dev
         self.band, self.group = band, group
+        self.peer = None
         self.use_hints = True
         H = cfg["H"]
         self.y0, self.y1 = (0, H) if band is None else T.sharding.band_pixel_rows(band, H)
@@ -195,7 +199,7 @@ class Stepper:
         color, radii, depth, alpha, resid = ras(
             p["means3D"], None, p["opacities"], shs=p["shs"], scales=p["scales"], rotations=p["rotations"],
             touch_depth=target, touch_weight=weight, depth_loss="l1", depth_loss_mult=DEPTH_LOSS_MULT,
-            depth_normalize=True, tile_rows=self.band, process_group=self.group,
+            depth_normalize=True, tile_rows=self.band, process_group=self.group, peer_exchange=self.peer,
             rendered_hint=self.hints.get(key, 0) if self.use_hints else 0)
         self.hints[key] = int(ras.last_num_rendered * 1.05) + 4096
         y0, y1 = self.y0, self.y1
@@ -272,6 +276,7 @@ class TrainStepper(Stepper):
                            depth_loss_type="DEPTH_UNCERTAINTY_WEIGHTED_LOSS", uncertainty_weight=1.0,
                            refine_every=refine_every, warmup_length=0)
         self.trainer = T.TouchGSTrainer(*raw, tc, process_group=group)
+        self.raw_n = int(raw[0].shape[0])
         self.n_history = [self.trainer.num_points]
 
     def _run(self, cam, view, proj, campos, gt, target, weight):
@@ -459,6 +464,17 @@ def main():
     else:
         stepper = Stepper(cfg, params, bg, dev, band, group)
     stepper.use_hints = not args.no_hints
+    exchange = "none"
+    if world > 1:
+        exchange = "nccl all-reduce"
+        if args.exchange == "p2p":
+            peer = T.sharding.make_peer_exchange(group, int(N * (3 if train_mode else 1)), dev)
+            if peer is not None:
+                peer.bands = T.sharding.even_bands(H, world)
+                stepper.peer = peer
+                if train_mode:
+                    stepper.trainer.peer = peer
+                exchange = "p2p gather fused into preprocess-backward (symmetric memory over NVLink), no all-reduce"
     # allocator priming (setup, not warm-up): every camera has its own instance count, so touch each
     # once so that torch's caching allocator owns blocks of every size before anything is timed
     for b in batches:
@@ -606,7 +622,7 @@ def main():
         "config": {"workload": f"{args.config}: {N} Gaussians, {W}x{H}, SH deg {cfg['sh_degree']}, fused touch depth-L1 "
                                f"(mult {DEPTH_LOSS_MULT}), {len(batches)} orbit cameras cycled",
                    "num_rendered_cam0": I_cam0, "visible_cam0": n_vis,
-                   "parallelism": "single GPU" if world == 1 else f"tile-row shard x{world} + 1 all-reduce of [N,10] fp32 per step",
+                   "parallelism": "single GPU" if world == 1 else f"tile-row shard x{world}; [N,10] fp32 screen-gradient exchange: {exchange}",
                    "rendered_hint": "off (synchronous sizing)" if args.no_hints else "per-view instance count of the previous visit +5% (speculative sizing; exact re-run on overflow)",
                    "l2_policy": "working set per step (params+grads 472 MB, instance records >250 MB) exceeds the 126 MB L2; no explicit flush"},
         "clocks": clocks,

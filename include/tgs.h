@@ -183,6 +183,20 @@ int tgs_backward_preprocess(const TgsSettings* s, const TgsGaussians* g, const T
                             const int32_t* radii, const float* screen_grads,
                             const TgsGrads* grads, void* stream);
 
+/*
+ * Multi-GPU form of tgs_backward_preprocess with the exchange FUSED into the kernel: rank r rendered
+ * the tile rows [peer_tile_rows_host[2r], peer_tile_rows_host[2r+1]) into ITS screen-gradient buffer
+ * peer_screen_grads_host[r] (device pointers valid on THIS device: peer-mapped / symmetric memory over NVLink,
+ * the local rank's own buffer included).  For every Gaussian the kernel reads the rows of exactly those ranks whose
+ * band its tile-row span touches and sums them in ascending rank order -- no all-reduce, no second kernel.
+ * The caller must have synchronised the ranks (all tgs_backward_render calls finished) before this runs.
+ */
+#define TGS_MAX_PEERS 8
+int tgs_backward_preprocess_gather(const TgsSettings* s, const TgsGaussians* g, const TgsSaved* saved,
+                                   const int32_t* radii, const float* const* peer_screen_grads_host,
+                                   const int32_t* peer_tile_rows_host, int32_t world,
+                                   const TgsGrads* grads, void* stream);
+
 /* replaces RasterizeGaussiansBackwardCUDA: tgs_backward_render + tgs_backward_preprocess. */
 int tgs_backward(const TgsSettings* s, const TgsGaussians* g, const TgsSaved* saved,
                  const int32_t* radii,

@@ -111,6 +111,9 @@ SIGNATURES = {
                                       c_fp, c_fp, c_fp, C.POINTER(TgsTouch), c_fp, c_fp, c_fp]),
     "tgs_backward_preprocess": (C.c_int, [C.POINTER(TgsSettings), C.POINTER(TgsGaussians), C.POINTER(TgsSaved),
                                           c_fp, c_fp, C.POINTER(TgsGrads), c_fp]),
+    "tgs_backward_preprocess_gather": (C.c_int, [C.POINTER(TgsSettings), C.POINTER(TgsGaussians), C.POINTER(TgsSaved),
+                                                 c_fp, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int32,
+                                                 C.POINTER(TgsGrads), c_fp]),
     "tgs_backward": (C.c_int, [C.POINTER(TgsSettings), C.POINTER(TgsGaussians), C.POINTER(TgsSaved), c_fp,
                                c_fp, c_fp, c_fp, C.POINTER(TgsTouch), c_fp, c_fp, C.POINTER(TgsGrads), c_fp]),
     "tgs_touch_loss_scale": (C.c_int, [c_fp, C.c_int64, C.c_float, C.c_float, c_fp, c_fp]),

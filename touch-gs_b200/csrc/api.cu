@@ -288,7 +288,31 @@ extern "C" int tgs_backward_preprocess(const TgsSettings* s, const TgsGaussians*
     if (g->cov3D_precomp && !grads->dcov3D) { tgs_set_error("dcov3D required when cov3D_precomp given"); return TGS_EINVAL; }
     const TgsCam cam = tgs_make_cam(s);
     GeomView gv = tgs_geom_view(saved->geom, g->N);
-    return tgs_launch_preprocess_bwd(cam, s, g, gv, radii, screen_grads, grads, (cudaStream_t)stream);
+    return tgs_launch_preprocess_bwd(cam, s, g, gv, radii, screen_grads, nullptr, nullptr, 0, grads, (cudaStream_t)stream);
+}
+
+extern "C" int tgs_backward_preprocess_gather(const TgsSettings* s, const TgsGaussians* g, const TgsSaved* saved,
+                                              const int32_t* radii, const float* const* peer_screen_grads_host,
+                                              const int32_t* peer_tile_rows_host, int32_t world,
+                                              const TgsGrads* grads, void* stream) {
+    int rc = check_inputs(s, g);
+    if (rc) return rc;
+    if (g->N == 0) return 0;
+    if (!saved || !saved->geom) { tgs_set_error("tgs_backward_preprocess_gather: saved buffers missing"); return TGS_ESTATE; }
+    if (world < 1 || world > TGS_MAX_PEERS || !peer_screen_grads_host || !peer_tile_rows_host) {
+        tgs_set_error("tgs_backward_preprocess_gather: world must be 1..%d with peer pointers and bands", TGS_MAX_PEERS); return TGS_EINVAL; }
+    for (int r = 0; r < world; ++r)
+        if (!peer_screen_grads_host[r]) { tgs_set_error("tgs_backward_preprocess_gather: peer %d pointer is NULL", r); return TGS_EINVAL; }
+    if (!radii || !grads || !grads->dmeans2D || !grads->dmeans3D || !grads->dopacity) {
+        tgs_set_error("tgs_backward_preprocess_gather: NULL gradient buffers"); return TGS_EINVAL; }
+    if (g->shs && !grads->dshs) { tgs_set_error("dshs required when shs given"); return TGS_EINVAL; }
+    if (g->colors_precomp && !grads->dcolors) { tgs_set_error("dcolors required when colors_precomp given"); return TGS_EINVAL; }
+    if (g->scales && (!grads->dscales || !grads->drotations)) { tgs_set_error("dscales/drotations required"); return TGS_EINVAL; }
+    if (g->cov3D_precomp && !grads->dcov3D) { tgs_set_error("dcov3D required when cov3D_precomp given"); return TGS_EINVAL; }
+    const TgsCam cam = tgs_make_cam(s);
+    GeomView gv = tgs_geom_view(saved->geom, g->N);
+    return tgs_launch_preprocess_bwd(cam, s, g, gv, radii, nullptr, peer_screen_grads_host, peer_tile_rows_host, world,
+                                     grads, (cudaStream_t)stream);
 }
 
 extern "C" int tgs_backward(const TgsSettings* s, const TgsGaussians* g, const TgsSaved* saved, const int32_t* radii,

@@ -100,8 +100,20 @@ k_preprocess(int N, const float* __restrict__ means, const float* __restrict__ s
     ids[i] = (uint32_t)i;
 }
 
+// Multi-GPU exchange FUSED into the consumer: instead of an all-reduce of the [N,10] screen-space
+// gradient buffers between BACKWARD::render and this kernel, every rank reads the partial sums straight out of its
+// peers' buffers over NVLink (P2P loads through NVSwitch) while it does the chain rule.  Every rank preprocesses all N
+// Gaussians, so each can tell from a Gaussian's (unclipped) tile-row span which ranks' bands it touches: only those
+// ranks' rows are read -- about one 40-byte row per Gaussian instead of the 2 x 40 B x (g-1)/g an all-reduce moves --
+// and they are summed in ascending rank order on every rank, so the replicas stay bit-identical.
+struct PeerGather {
+    int world;                                   // 0: single buffer (`sgrad`), no exchange
+    const float* ptr[TGS_MAX_PEERS];             // peer r's [N,10] partial screen-gradient buffer
+    int row0[TGS_MAX_PEERS], row1[TGS_MAX_PEERS];  // tile-row band rendered by rank r
+};
+
 __global__ void __launch_bounds__(kBlock)
-k_preprocess_bwd(int N, const float* __restrict__ means, const float* __restrict__ scales,
+k_preprocess_bwd(int N, PeerGather pg, const TgsRecord* __restrict__ rec, const float* __restrict__ means, const float* __restrict__ scales,
                  const float* __restrict__ rots, const float* __restrict__ shs,
                  const float* __restrict__ covpre, const float* __restrict__ vm,
                  const float* __restrict__ pm, const float* __restrict__ campos, TgsCam cam,
@@ -121,9 +133,21 @@ k_preprocess_bwd(int N, const float* __restrict__ means, const float* __restrict
     for (int k = 0; k < TGS_NGRAD; ++k) sg[k] = 0.0f;
     bool vis = radii[i] > 0;
     if (vis) {
-        const float2* s2 = reinterpret_cast<const float2*>(sgrad + (size_t)TGS_NGRAD * i);
+        if (pg.world == 0) {
+            const float2* s2 = reinterpret_cast<const float2*>(sgrad + (size_t)TGS_NGRAD * i);
 #pragma unroll
-        for (int k = 0; k < TGS_NGRAD / 2; ++k) { float2 v = s2[k]; sg[2 * k] = v.x; sg[2 * k + 1] = v.y; }
+            for (int k = 0; k < TGS_NGRAD / 2; ++k) { float2 v = s2[k]; sg[2 * k] = v.x; sg[2 * k + 1] = v.y; }
+        } else {
+            int y0, y1;                               // the Gaussian's tile rows in the FULL image (getRect, unclipped)
+            tgs_rect1(rec[i].a.y, (float)radii[i], cam.Ty, y0, y1);
+            for (int r = 0; r < pg.world; ++r) {
+                if (y0 < pg.row1[r] && y1 > pg.row0[r]) {
+                    const float2* s2 = reinterpret_cast<const float2*>(pg.ptr[r] + (size_t)TGS_NGRAD * i);
+#pragma unroll
+                    for (int k = 0; k < TGS_NGRAD / 2; ++k) { float2 v = s2[k]; sg[2 * k] += v.x; sg[2 * k + 1] += v.y; }
+                }
+            }
+        }
         float x = means[3 * i], y = means[3 * i + 1], z = means[3 * i + 2];
         float cov[6];
 #pragma unroll
@@ -188,12 +212,20 @@ int tgs_launch_preprocess(const TgsCam& cam, const TgsSettings* s, const TgsGaus
 
 int tgs_launch_preprocess_bwd(const TgsCam& cam, const TgsSettings* s, const TgsGaussians* g,
                               GeomView gv, const int32_t* radii, const float* screen_grads,
+                              const float* const* peer_grads, const int32_t* peer_rows, int world,
                               const TgsGrads* gr, cudaStream_t st) {
     int N = g->N;
     if (N == 0) return 0;
+    PeerGather pg;
+    pg.world = 0;
+    for (int r = 0; r < TGS_MAX_PEERS; ++r) { pg.ptr[r] = nullptr; pg.row0[r] = pg.row1[r] = 0; }
+    if (world > 0) {
+        pg.world = world;
+        for (int r = 0; r < world; ++r) { pg.ptr[r] = peer_grads[r]; pg.row0[r] = peer_rows[2 * r]; pg.row1[r] = peer_rows[2 * r + 1]; }
+    }
     TgsProfScope prof(TGS_STAGE_PREPROCESS_BWD, st);
     k_preprocess_bwd<<<(N + kBlock - 1) / kBlock, kBlock, 0, st>>>(
-        N, g->means3D, g->scales, g->rotations, g->shs, g->cov3D_precomp, s->viewmatrix,
+        N, pg, gv.records, g->means3D, g->scales, g->rotations, g->shs, g->cov3D_precomp, s->viewmatrix,
         s->projmatrix, s->campos, cam, gv.cov3D, gv.clamped, radii, screen_grads, gr->dmeans2D,
         gr->dmeans3D, gr->dopacity, g->shs ? gr->dshs : nullptr, gr->dcolors, gr->dscales,
         gr->drotations, gr->dcov3D);

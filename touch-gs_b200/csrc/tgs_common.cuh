@@ -80,8 +80,10 @@ size_t tgs_depth_sort_temp_bytes(int N);
 // preprocess.cu
 int tgs_launch_preprocess(const TgsCam& cam, const TgsSettings* s, const TgsGaussians* g,
                           GeomView gv, int32_t* radii, cudaStream_t st);
+// world > 0: gather the partial screen gradients from `peer_grads[0..world)` (bands in peer_rows[2r], [2r+1])
 int tgs_launch_preprocess_bwd(const TgsCam& cam, const TgsSettings* s, const TgsGaussians* g,
                               GeomView gv, const int32_t* radii, const float* screen_grads,
+                              const float* const* peer_grads, const int32_t* peer_rows, int world,
                               const TgsGrads* grads, cudaStream_t st);
 int tgs_launch_mark_visible(int N, const float* means, const float* vm, uint8_t* present, cudaStream_t st);
 // binning.cu

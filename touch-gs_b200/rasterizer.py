@@ -57,6 +57,7 @@ class TouchOptions(NamedTuple):
     rendered_hint: int = 0                         # > 0: speculative sizing (hides the forward's host sync)
     info: Optional[dict] = None                    # filled with num_rendered / capacity of the call
     touch_rows: Optional[Tuple[int, int]] = None   # pixel rows where the touch loss applies (None = all rows)
+    peer_exchange: object = None                   # sharding.PeerScreenGrads: fused P2P gather instead of all-reduce
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -298,11 +299,15 @@ class _RasterizeGaussians(torch.autograd.Function):
                                    scale=scale.data_ptr(), mode=L.LOSS_MODES[opt.depth_loss],
                                    row_begin=0 if opt.touch_rows is None else int(opt.touch_rows[0]),
                                    row_end=0 if opt.touch_rows is None else int(opt.touch_rows[1]))
-            sgrad = torch.empty((max(N, 1), L.NGRAD), dtype=torch.float32, device=dev)
+            peer = opt.peer_exchange if N > 0 else None
+            if peer is not None:
+                sgrad, peer_ptrs, peer_handle = peer.acquire(N)     # this rank's peer-mapped buffer of the step
+            else:
+                sgrad = torch.empty((max(N, 1), L.NGRAD), dtype=torch.float32, device=dev)
             L.check(lib.tgs_backward_render(C.byref(s), C.byref(g), C.byref(saved), _ptr(g_color), _ptr(g_depth),
                                             _ptr(g_alpha), None if touch is None else C.byref(touch), None,
                                             _ptr(sgrad), _stream_ptr(dev)), "tgs_backward_render")
-            if opt.process_group is not None:
+            if peer is None and opt.process_group is not None:
                 # the ONE exchange step of the multi-GPU path: sum the compact [N,10] screen-space
                 # gradients of all tile-row bands, NCCL over NVLink
                 import torch.distributed as dist
@@ -321,8 +326,16 @@ class _RasterizeGaussians(torch.autograd.Function):
                             dscales=None if dsc is None else dsc.data_ptr(),
                             drotations=None if drot is None else drot.data_ptr(),
                             dcov3D=None if dcov is None else dcov.data_ptr())
-            L.check(lib.tgs_backward_preprocess(C.byref(s), C.byref(g), C.byref(saved), _ptr(radii), _ptr(sgrad),
-                                                C.byref(gr), _stream_ptr(dev)), "tgs_backward_preprocess")
+            if peer is not None:
+                # FUSED exchange: wait until every rank has finished BACKWARD::render, then the chain-rule
+                # kernel gathers each Gaussian's partial sums straight from the owning peers' buffers over NVLink
+                peer_handle.barrier(channel=0)
+                L.check(lib.tgs_backward_preprocess_gather(C.byref(s), C.byref(g), C.byref(saved), _ptr(radii), peer_ptrs,
+                                                           peer.band_array(), peer.world, C.byref(gr), _stream_ptr(dev)),
+                        "tgs_backward_preprocess_gather")
+            else:
+                L.check(lib.tgs_backward_preprocess(C.byref(s), C.byref(g), C.byref(saved), _ptr(radii), _ptr(sgrad),
+                                                    C.byref(gr), _stream_ptr(dev)), "tgs_backward_preprocess")
         # autograd rejects a gradient for an input that was not a Variable (e.g. means2D=None)
         grads = (dmeans3D, dmeans2D, dsh, dcol, dopac.reshape(ctx.opacity_shape), dsc, drot, dcov)
         need = ctx.needs_input_grad
@@ -363,7 +376,7 @@ class GaussianRasterizer(torch.nn.Module):
                 rotations=None, cov3D_precomp=None, *, touch_depth=None, touch_weight=None,
                 depth_loss: str = "none", depth_loss_mult: float = 1.0, depth_normalize: bool = True,
                 depth_loss_norm: Optional[float] = None, tile_rows=None, process_group=None,
-                rendered_hint: int = 0, touch_rows=None):
+                rendered_hint: int = 0, touch_rows=None, peer_exchange=None):
         if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
             raise Exception("Please provide excatly one of either SHs or precomputed colors!")
         if ((scales is None or rotations is None) and cov3D_precomp is None) or \
@@ -372,7 +385,7 @@ class GaussianRasterizer(torch.nn.Module):
         e = _empty_on(means3D.device)
         info = {}
         opt = TouchOptions(touch_depth, touch_weight, depth_loss, depth_loss_mult, depth_normalize,
-                           depth_loss_norm, tile_rows, process_group, rendered_hint, info, touch_rows)
+                           depth_loss_norm, tile_rows, process_group, rendered_hint, info, touch_rows, peer_exchange)
         out = rasterize_gaussians(means3D, means2D,
                                   e if shs is None else shs, e if colors_precomp is None else colors_precomp,
                                   opacities, e if scales is None else scales, e if rotations is None else rotations,

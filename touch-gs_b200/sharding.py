@@ -55,3 +55,69 @@ def all_reduce_screen_grads(sgrad, group=None):
     import torch.distributed as dist
     dist.all_reduce(sgrad, op=dist.ReduceOp.SUM, group=group)
     return sgrad
+
+
+class PeerScreenGrads:
+    """Peer-mapped (symmetric-memory) [N,10] screen-gradient buffers for the FUSED exchange of the tile-row shard:
+    ``tgs_backward_preprocess_gather`` reads the partial sums straight out of every peer's buffer over NVLink, so
+    there is no all-reduce and no reduction kernel between BACKWARD::render and the per-Gaussian chain rule.
+
+    Two buffers are used alternately: rank A may still be reading rank B's buffer k while B already renders step
+    k+1 into the other one; B cannot reach step k+2 (which overwrites buffer k) before the barrier of step k+1, and
+    A only enters that barrier after its reads of step k have been enqueued ahead of it -- one barrier per step.
+
+    ``bands[r]`` = tile rows rank r renders (including any halo); set by the caller before each step.
+    torch's symmetric memory provides the allocation, the handle exchange and the barrier (plumbing); the gather
+    itself is our kernel."""
+
+    def __init__(self, group, max_gaussians: int, device, n_grad: int = 10):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > 8:
+            raise ValueError("PeerScreenGrads supports up to 8 ranks of one NVSwitch box")
+        self.capacity, self.n_grad = int(max_gaussians), n_grad
+        self.bufs, self.handles, self.ptr_arrays = [], [], []
+        name = self.group.group_name
+        try:
+            symm.enable_symm_mem_for_group(name)       # required by older torch, a deprecated no-op in newer ones
+        except Exception:  # noqa: BLE001
+            pass
+        for _ in range(2):
+            t = symm.empty(self.capacity * n_grad, dtype=torch.float32, device=device)
+            h = symm.rendezvous(t, name)
+            ptrs = [int(p) for p in h.buffer_ptrs]
+            self.bufs.append(t)
+            self.handles.append(h)
+            self.ptr_arrays.append((C.c_void_p * self.world)(*ptrs))
+        self.k = 0
+        self.bands = None
+
+    def acquire(self, N: int):
+        """-> (this step's [N,10] buffer of THIS rank, ctypes array of all ranks' pointers, barrier handle)"""
+        if N > self.capacity:
+            raise ValueError(f"PeerScreenGrads capacity {self.capacity} < {N} Gaussians")
+        i = self.k & 1
+        self.k += 1
+        return self.bufs[i][: N * self.n_grad].view(N, self.n_grad), self.ptr_arrays[i], self.handles[i]
+
+    def band_array(self):
+        import ctypes as C
+        if self.bands is None or len(self.bands) != self.world:
+            raise ValueError("PeerScreenGrads.bands must list the rendered tile rows of every rank")
+        flat = [int(v) for b in self.bands for v in b]
+        return (C.c_int32 * (2 * self.world))(*flat)
+
+
+def make_peer_exchange(group, max_gaussians: int, device):
+    """PeerScreenGrads if symmetric memory works on this box (NVLink P2P between all ranks), else None (the caller
+    then uses the NCCL all-reduce path).  Both paths are GPU paths of this library; there is no CPU fallback."""
+    try:
+        return PeerScreenGrads(group, max_gaussians, device)
+    except Exception as e:  # noqa: BLE001
+        import warnings
+        warnings.warn(f"symmetric-memory peer exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduce")
+        return None

@@ -221,7 +221,7 @@ class TouchGSTrainer:
     [N,10] screen-space gradients are summed once, and every rank applies the identical Adam / refine update."""
 
     def __init__(self, means, shs, opacity_logit, scales_log, quats, cfg: Optional[TrainConfig] = None,
-                 process_group=None):
+                 process_group=None, peer_exchange=None):
         self.cfg = cfg or TrainConfig()
         if self.cfg.depth_loss_type not in DEPTH_LOSS_TYPES:
             raise ValueError(f"depth_loss_type must be one of {DEPTH_LOSS_TYPES}")
@@ -232,6 +232,7 @@ class TouchGSTrainer:
         self.m = {k: torch.zeros_like(v) for k, v in self.p.items()}
         self.v = {k: torch.zeros_like(v) for k, v in self.p.items()}
         self.group = process_group
+        self.peer = peer_exchange              # sharding.PeerScreenGrads: fused P2P gather instead of the all-reduce
         self.step = 0
         self._reset_stats()
         self.gen = torch.Generator(device=self.dev).manual_seed(self.cfg.seed)
@@ -259,10 +260,11 @@ class TouchGSTrainer:
         import torch.distributed as dist
         world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         Ty = (H + TILE - 1) // TILE
-        b0, b1 = sharding.even_bands(H, world)[rank]
-        y0, y1 = sharding.band_pixel_rows((b0, b1), H)
-        e0, e1 = max(0, b0 - 1), min(Ty, b1 + 1)                       # + one tile row of halo on each side
-        return (e0, e1), (y0, y1), sharding.band_pixel_rows((e0, e1), H)
+        own = sharding.even_bands(H, world)
+        ext = [(max(0, b0 - 1), min(Ty, b1 + 1)) for b0, b1 in own]    # + one tile row of halo on each side
+        if self.peer is not None:
+            self.peer.bands = ext
+        return ext[rank], sharding.band_pixel_rows(own[rank], H), sharding.band_pixel_rows(ext[rank], H)
 
     def touch_weight(self, touch_weight):
         """SIMPLE_LOSS: unweighted.  DEPTH_UNCERTAINTY_WEIGHTED_LOSS: w = (1/sigma) / uncertainty_weight, the
@@ -294,7 +296,7 @@ class TouchGSTrainer:
                 means, means2D, opac, shs=shs, scales=scales, rotations=rot,
                 touch_depth=touch_depth, touch_weight=w, depth_loss=(cfg.depth_loss if touch_depth is not None else "none"),
                 depth_loss_mult=cfg.depth_loss_mult, depth_normalize=True, tile_rows=tile_rows, process_group=self.group,
-                touch_rows=loss_rows, rendered_hint=self.hints.get(view_key, 0) if view_key is not None else 0)
+                touch_rows=loss_rows, peer_exchange=self.peer, rendered_hint=self.hints.get(view_key, 0) if view_key is not None else 0)
             if view_key is not None:
                 self.hints[view_key] = int(ras.last_num_rendered * 1.05) + 4096
             loss = photometric_loss(color, gt_rgb, cfg.ssim_lambda, loss_rows, grad_rows)
