@@ -203,7 +203,10 @@ class Stepper:
             rendered_hint=self.hints.get(key, 0) if self.use_hints else 0)
         self.hints[key] = int(ras.last_num_rendered * 1.05) + 4096
         y0, y1 = self.y0, self.y1
-        loss = (color[:, y0:y1] - gt[:, y0:y1]).abs().sum() * self.inv      # mean |C - C*| (band-local part)
+        # mean |C - C*| (band-local part) through the library's fused photometric loss (lambda_dssim = 0: plain L1,
+        # one kernel forward, one backward)
+        rows = None if self.band is None else (y0, y1)
+        loss = T.photometric_loss(color, gt, 0.0, rows, rows)
         loss.backward()
         return loss
 
@@ -211,17 +214,36 @@ class Stepper:
         d = b["dev"]
         return self._run(b["cam"], d["view"], d["proj"], d["campos"], d["gt"], d["target"], d["weight"])
 
+    def copy_rows(self):
+        """Image rows of the per-step inputs this rank needs on its GPU: its own band (rasterizer workload) or its
+        band plus the one-tile halo the SSIM window reaches into (train step); everything on a single GPU."""
+        return self.y0, self.y1
+
     def _prefetch(self, b, slot):
-        """H2D of one step's inputs from pinned host memory on the copy stream."""
+        """H2D of one step's inputs from pinned host memory on the copy stream.  A rank of the tile-row shard copies
+        only the image rows it consumes (ground truth, touch depth and weight of its band); cameras are copied whole."""
+        r0, r1 = self.copy_rows()
         with torch.cuda.stream(self.copy_stream):
             for k, v in b["host"].items():
-                self.stage[slot][k].copy_(v, non_blocking=True)
+                if k in ("gt", "target", "weight") and (r0, r1) != (0, self.cfg["H"]):
+                    self.stage[slot][k][..., r0:r1, :].copy_(v[..., r0:r1, :], non_blocking=True)
+                else:
+                    self.stage[slot][k].copy_(v, non_blocking=True)
             self.ready[slot].record(self.copy_stream)
+
+    def h2d_bytes_rank(self, b):
+        r0, r1 = self.copy_rows()
+        H = self.cfg["H"]
+        tot = 0
+        for k, v in b["host"].items():
+            n = v.numel() * v.element_size()
+            tot += n * (r1 - r0) // H if k in ("gt", "target", "weight") else n
+        return int(tot)
 
     def e2e_begin(self, batches):
         h = batches[0]["host"]
         self.copy_stream = torch.cuda.Stream(device=self.dev)
-        self.stage = [{k: torch.empty_like(v, device=self.dev) for k, v in h.items()} for _ in range(2)]
+        self.stage = [{k: torch.zeros_like(v, device=self.dev) for k, v in h.items()} for _ in range(2)]
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]
         self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
         self.loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
@@ -278,6 +300,11 @@ class TrainStepper(Stepper):
         self.trainer = T.TouchGSTrainer(*raw, tc, process_group=group)
         self.raw_n = int(raw[0].shape[0])
         self.n_history = [self.trainer.num_points]
+
+    def copy_rows(self):
+        if self.group is None:
+            return 0, self.cfg["H"]
+        return self.trainer._bands(self.cfg["H"])[2]          # band + halo rows
 
     def _run(self, cam, view, proj, campos, gt, target, weight):
         T, cfg = self.T, self.cfg
@@ -541,11 +568,16 @@ def main():
     if not args.no_e2e:
         stepper.e2e_begin(batches)
         ms_e, clocks_e, _, _ = timed(stepper.e2e_step, steps, warmup, finalize=stepper.e2e_finish)
+        h2d_total = stepper.h2d_bytes_rank(batches[0])
+        if world > 1:                                   # whole-job bytes: every rank copies its own rows + the cameras
+            tb = torch.tensor([float(h2d_total)], device=dev, dtype=torch.float64)
+            torch.distributed.all_reduce(tb)
+            h2d_total = int(tb.item())
         e2e = {"value": N * steps / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e / steps,
                "losses_read": len(stepper.losses), "clocks": clocks_e,
-               "h2d_bytes_per_step": Stepper.h2d_bytes(batches[0]), "d2h_bytes_per_step": 4,
+               "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": 4 * world,
                "what": "GaussianRasterizer fwd + L1 photometric + fused touch depth-L1 bwd; per-step camera, GT image, "
-                       "touch depth and weight copied H2D from pinned host memory (copy stream, issued one step ahead, "
+                       "touch depth and weight (each rank: the image rows of its band) copied H2D from pinned host memory (copy stream, issued one step ahead, "
                        "double-buffered); loss copied D2H every step and read by the host one step later; Gaussian "
                        "parameters are resident training state"}
 

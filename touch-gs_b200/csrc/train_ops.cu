@@ -165,6 +165,40 @@ k_ssim_bwd(const float* __restrict__ color, const float* __restrict__ gt, const 
     }
 }
 
+// lambda_dssim == 0: the loss is the plain L1 mean -- two streaming passes (sum, then sign), 16-byte accesses.
+__global__ void __launch_bounds__(256)
+k_l1_fwd(const float* __restrict__ color, const float* __restrict__ gt, int W, int H, int y_begin, int y_end,
+         double* __restrict__ sums) {
+    __shared__ float red[8];
+    const int64_t row_elems = (int64_t)W * (y_end - y_begin);
+    const int64_t n = 3 * row_elems, stride = (int64_t)gridDim.x * blockDim.x;
+    const size_t HW = (size_t)W * H;
+    float acc = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int ch = (int)(i / row_elems);
+        const size_t o = ch * HW + (size_t)y_begin * W + (size_t)(i - ch * row_elems);
+        acc += fabsf(color[o] - gt[o]);
+    }
+    const float b = block_sum_256(acc, red);
+    if (threadIdx.x == 0) atomicAdd(sums, (double)b);
+}
+__global__ void __launch_bounds__(256)
+k_l1_bwd(const float* __restrict__ color, const float* __restrict__ gt, int W, int H, int y_begin, int y_end,
+         int o_begin, int o_end, float inv_n, const float* __restrict__ grad_out, float* __restrict__ dcolor) {
+    const int64_t row_elems = (int64_t)W * (o_end - o_begin);
+    const int64_t n = 3 * row_elems, stride = (int64_t)gridDim.x * blockDim.x;
+    const size_t HW = (size_t)W * H;
+    const float g = (grad_out ? grad_out[0] : 1.0f) * inv_n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int ch = (int)(i / row_elems);
+        const int64_t r = i - ch * row_elems;
+        const size_t o = ch * HW + (size_t)o_begin * W + (size_t)r;
+        const int py = o_begin + (int)(r / W);
+        const float x = color[o], y = gt[o];
+        dcolor[o] = (py >= y_begin && py < y_end) ? g * (float)((x > y) - (x < y)) : 0.0f;
+    }
+}
+
 // -------------------------------------------------------------------------------- activations
 __global__ void __launch_bounds__(256)
 k_activate_fwd(int N, const float* __restrict__ scales_log, const float* __restrict__ quats,
@@ -363,6 +397,12 @@ extern "C" int tgs_photometric_loss_forward(const float* color, const float* gt,
     TgsProfScope prof(TGS_STAGE_PHOTO_FWD, st);
     TGS_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(double), st));
     dim3 grid((W + kST - 1) / kST, (row_end - row_begin + kST - 1) / kST, 3);
+    if (lambda_dssim == 0.0f) {                     // plain L1: no SSIM pass, no derivative maps
+        const int64_t n = 3ll * W * (row_end - row_begin);
+        int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        k_l1_fwd<<<(unsigned)blocks, 256, 0, st>>>(color, gt, W, H, row_begin, row_end, sums);
+    } else
     k_ssim_fwd<<<grid, 256, 0, st>>>(color, gt, W, H, row_begin, row_end, taps, dmaps, sums);
     k_loss_finish<<<1, 1, 0, st>>>(sums, 3.0 * W * (double)(row_end - row_begin), 3.0 * W * (double)H, lambda_dssim, loss_out);
     tgs_count_own(2);
@@ -381,6 +421,13 @@ extern "C" int tgs_photometric_loss_backward(const float* color, const float* gt
     static const SsimTaps taps = make_taps();
     dim3 grid((W + kST - 1) / kST, (out_row_end - out_row_begin + kST - 1) / kST, 3);
     TgsProfScope prof(TGS_STAGE_PHOTO_BWD, st);
+    if (lambda_dssim == 0.0f) {
+        const int64_t n = 3ll * W * (out_row_end - out_row_begin);
+        int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        k_l1_bwd<<<(unsigned)blocks, 256, 0, st>>>(color, gt, W, H, row_begin, row_end, out_row_begin, out_row_end,
+                                                   (float)(1.0 / (3.0 * W * (double)H)), grad_out, dL_dcolor);
+    } else
     k_ssim_bwd<<<grid, 256, 0, st>>>(color, gt, dmaps, W, H, row_begin, row_end, out_row_begin, out_row_end, taps,
                                      lambda_dssim, (float)(1.0 / (3.0 * W * (double)H)), grad_out, dL_dcolor);
     tgs_count_own(1);
