@@ -40,7 +40,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c5"])
+    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c5", "fixture", "fixture1m"],
+                    help="fixture*: Gaussians seeded from the reference's sample point cloud + its sample camera poses "
+                         "(tests/golden/fixture_scene.npz; SURVEY §8f N4), z-buffer depth of the cloud as the touch target")
     ap.add_argument("--num-gaussians", type=int, default=None, help="override N (development only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -51,6 +53,9 @@ def parse():
                          "full Touch-GS train step (activations, rasterizer, L1+SSIM loss, fused touch depth-L1, Adam, refine "
                          "every --refine-every steps: SURVEY §8f N1 / BASELINE config c5); neither is the headline metric")
     ap.add_argument("--refine-every", type=int, default=100)
+    ap.add_argument("--forward-only", action="store_true",
+                    help="eval / render path (reference experiment_utils/run_eval.py:43-48 -> ns-eval, ns-render): forward only, "
+                         "no grad, markVisible prefiltering; a secondary line, not the headline metric")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU exchange of the [N,10] screen gradients: p2p = gather fused into the preprocess-backward "
                          "kernel over peer-mapped memory (NVLink); nccl = one all-reduce (also the fallback if p2p is unavailable)")
@@ -143,8 +148,13 @@ def alg_bytes(N, I, P, T, K):
 def make_workload(cfg, N, n_cams, dev, rank, band, seed=0):
     import touchgs_b200 as T
     synth = T.synth
-    scene = synth.make_scene(N, cfg["sh_degree"], cfg["smin"], cfg["smax"], seed)
-    cams = synth.orbit_cameras(cfg["W"], cfg["H"], n_cams, 3.0, seed)
+    fixture = "fixture_copies" in cfg
+    if fixture:
+        scene = synth.fixture_scene(cfg["sh_degree"], cfg["fixture_copies"], seed)
+        cams = synth.fixture_cameras(cfg["W"], cfg["H"], n_cams)
+    else:
+        scene = synth.make_scene(N, cfg["sh_degree"], cfg["smin"], cfg["smax"], seed)
+        cams = synth.orbit_cameras(cfg["W"], cfg["H"], n_cams, 3.0, seed)
     H, W = cfg["H"], cfg["W"]
     params = {k: getattr(scene, k).to(dev).requires_grad_(True) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
     pert = synth.perturbed(scene, 0.01, seed)
@@ -154,11 +164,18 @@ def make_workload(cfg, N, n_cams, dev, rank, band, seed=0):
     for ci, cam in enumerate(cams):
         rs = T.GaussianRasterizationSettings(H, W, cam.tanfovx, cam.tanfovy, bg, 1.0, cam.viewmatrix.to(dev),
                                              cam.projmatrix.to(dev), cfg["sh_degree"], cam.campos.to(dev), False, False)
-        with torch.no_grad():      # touch target = expected depth of the PERTURBED scene, rendered by us
-            _, _, d, _, _ = T.GaussianRasterizer(rs)(pert.means3D.to(dev), None, pert.opacities.to(dev),
-                                                     shs=pert.shs.to(dev), scales=pert.scales.to(dev),
-                                                     rotations=pert.rotations.to(dev))
-        target, weight = synth.make_touch_maps(d[0].cpu(), seed=seed + ci)
+        if fixture:
+            # touch target = z-buffer depth image of the seed cloud (reference read_point_cloud.py:224-266), mm-quantised,
+            # 0 = no point; weight = 1/sigma with the touch sigma on the hit pixels
+            zb = synth.zbuffer_depth(scene.means3D[: 71_283], cam)
+            target = torch.round(zb * 1000.0).clamp(0, 65535) / 1000.0
+            weight = torch.where(target > 0, torch.full_like(target, 1.0 / 0.005), torch.zeros_like(target))
+        else:
+            with torch.no_grad():      # touch target = expected depth of the PERTURBED scene, rendered by us
+                _, _, d, _, _ = T.GaussianRasterizer(rs)(pert.means3D.to(dev), None, pert.opacities.to(dev),
+                                                         shs=pert.shs.to(dev), scales=pert.scales.to(dev),
+                                                         rotations=pert.rotations.to(dev))
+            target, weight = synth.make_touch_maps(d[0].cpu(), seed=seed + ci)
         gt = torch.rand(3, H, W, generator=g)
         host = dict(gt=gt.pin_memory(), target=target.pin_memory(), weight=weight.pin_memory(),
                     view=cam.viewmatrix.contiguous().pin_memory(), proj=cam.projmatrix.contiguous().pin_memory(),
@@ -210,7 +227,23 @@ class Stepper:
         loss.backward()
         return loss
 
+    def forward_only_step(self, b):
+        """The eval / render path: markVisible, then the forward of the operator under no_grad."""
+        T, cfg, p, d, cam = self.T, self.cfg, self.p, b["dev"], b["cam"]
+        rs = T.GaussianRasterizationSettings(cfg["H"], cfg["W"], cam.tanfovx, cam.tanfovy, self.bg, 1.0, d["view"], d["proj"],
+                                             cfg["sh_degree"], d["campos"], True, False)
+        with torch.no_grad():
+            ras = T.GaussianRasterizer(rs)
+            vis = ras.markVisible(p["means3D"])
+            color, radii, depth, alpha, _ = ras(p["means3D"], None, p["opacities"], shs=p["shs"], scales=p["scales"],
+                                                rotations=p["rotations"], tile_rows=self.band,
+                                                rendered_hint=self.hints.get(id(cam), 0) if self.use_hints else 0)
+            self.hints[id(cam)] = int(ras.last_num_rendered * 1.05) + 4096
+        return color, vis
+
     def device_step(self, b):
+        if getattr(self, "forward_only", False):
+            return self.forward_only_step(b)
         d = b["dev"]
         return self._run(b["cam"], d["view"], d["proj"], d["campos"], d["gt"], d["target"], d["weight"])
 
@@ -491,6 +524,9 @@ def main():
     else:
         stepper = Stepper(cfg, params, bg, dev, band, group)
     stepper.use_hints = not args.no_hints
+    stepper.forward_only = bool(args.forward_only) and not train_mode
+    if stepper.forward_only:
+        args.no_e2e = args.no_refcuda = args.no_cpu_baseline = True
     exchange = "none"
     if world > 1:
         exchange = "nccl all-reduce"
@@ -561,6 +597,7 @@ def main():
                                            shs=params["shs"].detach(), scales=params["scales"].detach(),
                                            rotations=params["rotations"].detach(), opt=T.TouchOptions(tile_rows=band))
         I_cam0 = int(st["num_rendered"])
+        live_cam0 = int((st["ranges_live"][:, 1] - st["ranges_live"][:, 0]).long().sum())
         n_vis = int((st["radii"] > 0).sum())
         del st
 
@@ -653,7 +690,7 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.config}: {N} Gaussians, {W}x{H}, SH deg {cfg['sh_degree']}, fused touch depth-L1 "
                                f"(mult {DEPTH_LOSS_MULT}), {len(batches)} orbit cameras cycled",
-                   "num_rendered_cam0": I_cam0, "visible_cam0": n_vis,
+                   "num_rendered_cam0": I_cam0, "live_instances_cam0": live_cam0, "visible_cam0": n_vis,
                    "parallelism": "single GPU" if world == 1 else f"tile-row shard x{world}; [N,10] fp32 screen-gradient exchange: {exchange}",
                    "rendered_hint": "off (synchronous sizing)" if args.no_hints else "per-view instance count of the previous visit +5% (speculative sizing; exact re-run on overflow)",
                    "l2_policy": "working set per step (params+grads 472 MB, instance records >250 MB) exceeds the 126 MB L2; no explicit flush"},
@@ -667,6 +704,8 @@ def main():
         "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved_GBps": step_bytes / (ms / steps * 1e-3) / 1e9,
                           "frac": step_bytes / (ms / steps * 1e-3) / 1e9 / peak},
     }
+    if stepper.forward_only:
+        out["metric"] = "forward-only Gaussians/sec (eval / render path: markVisible + operator forward under no_grad)"
     if train_mode:
         out["config"]["workload"] = (f"train_step on {args.config}: {N} Gaussians initially, {W}x{H}, SH deg {cfg['sh_degree']}, "
                                      f"L1+SSIM (lambda 0.2) + fused touch depth-L1 (uncertainty-weighted, mult {DEPTH_LOSS_MULT}), "

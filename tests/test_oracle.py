@@ -144,3 +144,29 @@ def test_golden_regression_fixture():
     np.testing.assert_allclose(z["depth"], out.depth.detach().numpy(), rtol=1e-5, atol=1e-6)
     for k, g in grads.items():
         np.testing.assert_allclose(z["grad_" + k], g.numpy(), rtol=2e-4, atol=1e-6 * float(np.abs(z["grad_" + k]).max()))
+
+
+def test_fixture_scene_and_zbuffer_match_reference_function():
+    """the fixture loader, and the z-buffer depth target against golden vectors produced by the
+    reference's own ``project_points_with_colors`` (tests/golden/make_zbuffer_golden.py)."""
+    import os
+    import numpy as np
+    from helpers import ROOT, T
+    sc = T.synth.fixture_scene(0)
+    assert sc.means3D.shape == (71283, 3) and sc.shs.shape == (71283, 1, 3)
+    assert float(sc.scales.min()) > 0 and torch.allclose(sc.rotations.norm(dim=-1), torch.ones(71283), atol=1e-5)
+    big = T.synth.fixture_scene(1, copies=3)
+    assert big.means3D.shape[0] == 3 * 71283 and torch.equal(big.means3D[:71283], sc.means3D)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "zbuffer_reference.npz"))
+    W, H = 160, 120
+    cams = T.synth.fixture_cameras(W, H, 3)
+    for i, cam in enumerate(cams):
+        got = T.synth.zbuffer_depth(sc.means3D[::7], cam)
+        ref = torch.from_numpy(z[f"depth_{i}"])
+        assert got.shape == ref.shape and float((ref > 0).float().mean()) > 0.01
+        assert torch.equal(got > 0, ref > 0), "z-buffer coverage differs from the reference function"
+        assert torch.allclose(got, ref, rtol=1e-6, atol=1e-6)
+        # every camera looks at the common focus of the 100 sample poses
+        f = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "fixture_scene.npz"))["focus"])
+        v = cam.viewmatrix.t() @ torch.cat([f, torch.ones(1)])
+        assert abs(float(v[0])) < 1e-4 and abs(float(v[1])) < 1e-4 and 0.3 < float(v[2]) < 0.8

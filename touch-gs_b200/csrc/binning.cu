@@ -94,10 +94,11 @@ k_ranges(int64_t I_host, const uint32_t* __restrict__ I_dev, int64_t cap, const 
 // array (ordered block compaction: ballot + warp prefix), remembering each record's position in the full list
 // (c.w) so that n_contrib is still reported in the spec'd indexing.  Results are bit-identical; the packed lists,
 // their TMA staging and the per-warp cull work shrink by the live fraction.
+constexpr int kPackItems = 4;          // instances per thread per round: four independent gathers in flight
 __global__ void __launch_bounds__(256)
 k_pack_live(const uint2* __restrict__ ranges, uint2* __restrict__ ranges_live, const uint32_t* __restrict__ vals,
             const float4* __restrict__ rec_in, float4* __restrict__ rec_out, int Tx) {
-    __shared__ uint32_t wcount[8];
+    __shared__ uint32_t wcount[kPackItems][8];
     const int tile = blockIdx.x;
     const uint2 rng = ranges[tile];
     const int len = (int)(rng.y - rng.x);
@@ -106,28 +107,41 @@ k_pack_live(const uint2* __restrict__ ranges, uint2* __restrict__ ranges_live, c
     const float x0 = (float)((tile % Tx) * TGS_TILE), y0 = (float)((tile / Tx) * TGS_TILE);
     const float x1 = x0 + (float)(TGS_TILE - 1), y1 = y0 + (float)(TGS_TILE - 1);
     uint32_t base = 0;
-    for (int c0 = 0; c0 < len; c0 += 256) {
-        const int j = c0 + tid;
-        bool live = false;
-        float4 a, b, c;
-        if (j < len) {
-            const float4* src = rec_in + (size_t)3 * vals[rng.x + j];
-            a = __ldg(src); b = __ldg(src + 1); c = __ldg(src + 2);
-            live = rect_may_touch(a, b, c.w, x0, x1, y0, y1);      // per-Gaussian record: c.w = -ln(255 o)
-        }
-        const unsigned m = __ballot_sync(kFull, live);
-        if (lane == 0) wcount[warp] = __popc(m);
-        __syncthreads();
-        uint32_t before = 0, total = 0;
+    for (int c0 = 0; c0 < len; c0 += 256 * kPackItems) {
+        float4 a[kPackItems], b[kPackItems];
+        const float4* src[kPackItems];
+        unsigned m[kPackItems];
 #pragma unroll
-        for (int w = 0; w < 8; ++w) { const uint32_t n = wcount[w]; total += n; if (w < warp) before += n; }
-        if (live) {
-            const uint32_t pos = base + before + __popc(m & ((1u << lane) - 1u));
-            float4* dst = rec_out + (size_t)3 * (rng.x + pos);
-            c.w = __int_as_float(j);                               // position in the tile's full sorted list
-            dst[0] = a; dst[1] = b; dst[2] = c;
+        for (int k = 0; k < kPackItems; ++k) {                     // list position of item k: c0 + k*256 + tid (coalesced)
+            const int j = c0 + k * 256 + tid;
+            src[k] = rec_in + (size_t)3 * (j < len ? vals[rng.x + j] : 0u);
         }
-        base += total;
+#pragma unroll
+        for (int k = 0; k < kPackItems; ++k)
+            if (c0 + k * 256 + tid < len) { a[k] = __ldg(src[k]); b[k] = __ldg(src[k] + 1); }
+#pragma unroll
+        for (int k = 0; k < kPackItems; ++k) {
+            const bool live = (c0 + k * 256 + tid < len) && rect_may_touch(a[k], b[k], splat_thr(b[k].w), x0, x1, y0, y1);
+            m[k] = __ballot_sync(kFull, live);
+            if (lane == 0) wcount[k][warp] = __popc(m[k]);
+        }
+        __syncthreads();
+        uint32_t run = base;
+#pragma unroll
+        for (int k = 0; k < kPackItems; ++k) {
+            uint32_t before = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { const uint32_t n = wcount[k][w]; total += n; if (w < warp) before += n; }
+            if (m[k] & (1u << lane)) {
+                const uint32_t pos = run + before + __popc(m[k] & ((1u << lane) - 1u));
+                float4* dst = rec_out + (size_t)3 * (rng.x + pos);
+                float4 c = __ldg(src[k] + 2);
+                c.w = __int_as_float(c0 + k * 256 + tid);          // position in the tile's full sorted list
+                dst[0] = a[k]; dst[1] = b[k]; dst[2] = c;
+            }
+            run += total;
+        }
+        base = run;
         __syncthreads();
     }
     if (tid == 0) ranges_live[tile] = make_uint2(rng.x, rng.x + base);

@@ -27,6 +27,9 @@ CONFIGS = {
     "c2": dict(N=100_000, W=800, H=800, sh_degree=3, smin=0.004, smax=0.04),
     "c3": dict(N=1_000_000, W=1920, H=1080, sh_degree=3, smin=0.002, smax=0.02),
     "c5": dict(N=5_000_000, W=3840, H=2160, sh_degree=3, smin=0.002, smax=0.02),
+    # Gaussians seeded from the reference's sample point cloud, cameras from its sample poses
+    "fixture": dict(N=71_283, W=800, H=800, sh_degree=3, smin=0.0, smax=0.0, fixture_copies=1),
+    "fixture1m": dict(N=71_283 * 14, W=1920, H=1080, sh_degree=3, smin=0.0, smax=0.0, fixture_copies=14),
 }
 
 
@@ -145,3 +148,86 @@ def config_scene(name: str, seed: int = 0, N: Optional[int] = None):
     scene = make_scene(n, c["sh_degree"], c["smin"], c["smax"], seed)
     cams = orbit_cameras(c["W"], c["H"], 8, 3.0, seed)
     return scene, cams
+
+
+# ------------------------------------------------------------------ realistic fixture
+def _fixture_path(path: Optional[str] = None) -> str:
+    import os
+    return path or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                                "fixture_scene.npz")
+
+
+def fixture_scene(sh_degree: int = 3, copies: int = 1, seed: int = 0, path: Optional[str] = None) -> Scene:
+    """Gaussians initialised from the reference's sample point cloud (``sample_pc_data/sparse.ply``, 71 283 coloured
+    points; committed as ``tests/golden/fixture_scene.npz`` by ``tests/golden/make_fixture_scene.py``) the way the
+    splat trainers of that era seed a scene: mean = point, isotropic scale = mean distance to the 3 nearest
+    neighbours, opacity 0.1, SH DC = (rgb - 0.5)/C0, higher bands 0, random orientation.
+    ``copies`` > 1 replicates every point with a jitter of its own neighbour distance (a denser cloud with the same
+    spatial distribution: 14 copies ~ 1M Gaussians)."""
+    import numpy as np
+    z = np.load(_fixture_path(path))
+    g = torch.Generator().manual_seed(seed)
+    pts = torch.from_numpy(z["points"]).float()
+    col = torch.from_numpy(z["colors"]).float() / 255.0
+    knn = torch.from_numpy(z["knn_dist"]).float().clamp_min(1e-4)
+    if copies > 1:
+        pts = pts.repeat(copies, 1)
+        col = col.repeat(copies, 1)
+        knn = knn.repeat(copies)
+        jit = torch.randn(pts.shape, generator=g) * knn[:, None]
+        jit[: z["points"].shape[0]] = 0.0
+        pts = pts + jit
+        knn = knn / float(copies) ** (1.0 / 3.0)
+    N = pts.shape[0]
+    K = (sh_degree + 1) ** 2
+    shs = torch.zeros(N, K, 3)
+    shs[:, 0] = (col - 0.5) / SH_C0
+    q = torch.randn(N, 4, generator=g)
+    q = q / q.norm(dim=-1, keepdim=True)
+    return Scene(pts.contiguous(), knn[:, None].repeat(1, 3).contiguous(), q.contiguous(),
+                 torch.full((N, 1), 0.1), shs.contiguous(), sh_degree)
+
+
+def fixture_cameras(W: int, H: int, n: int = 8, path: Optional[str] = None, znear: float = 0.01, zfar: float = 100.0):
+    """The first ``n`` (of 100, evenly strided) poses of the reference's ``sample_blender_data/transforms_train.json``
+    with its ``camera_angle_x``.  Blender / OpenGL camera-to-world (x right, y up, looking down -z) -> our view
+    convention (+z forward, +y down) with the diag(1,-1,-1) flip of reference
+    ``utils/create_point_cloud_from_touches.py:64``."""
+    import numpy as np
+    z = np.load(_fixture_path(path))
+    poses = torch.from_numpy(z["poses_c2w"]).double()
+    ang = float(z["camera_angle_x"])
+    idx = torch.linspace(0, poses.shape[0] - 1, n).round().long()
+    flip = torch.diag(torch.tensor([1.0, -1.0, -1.0, 1.0], dtype=torch.float64))
+    tanx = math.tan(0.5 * ang)
+    tany = tanx * H / W
+    cams = []
+    for i in idx.tolist():
+        V = flip @ torch.linalg.inv(poses[i])
+        P = torch.zeros(4, 4, dtype=torch.float64)
+        P[0, 0], P[1, 1] = 1.0 / tanx, 1.0 / tany
+        P[2, 2], P[2, 3], P[3, 2] = zfar / (zfar - znear), -(zfar * znear) / (zfar - znear), 1.0
+        cams.append(Camera(W, H, tanx, tany, V.t().contiguous().float(), (P @ V).t().contiguous().float(),
+                           poses[i][:3, 3].float()))
+    return cams
+
+
+def zbuffer_depth(points: torch.Tensor, cam: Camera) -> torch.Tensor:
+    """Point-cloud -> depth image by z-buffering, the logic of reference
+    ``data_preprocessing/vision/point_cloud/read_point_cloud.py:224-266`` (``project_points_with_colors``): pinhole
+    projection with fx = W / (2 tan(fovx/2)), principal point at the image centre, ``int()`` truncation of (u, v),
+    nearest depth wins, 0 where no point lands."""
+    W, H = cam.image_width, cam.image_height
+    V = cam.viewmatrix.t().double()
+    pc = points.double() @ V[:3, :3].t() + V[:3, 3]
+    fx, fy = W / (2.0 * cam.tanfovx), H / (2.0 * cam.tanfovy)
+    ok = pc[:, 2] > 0
+    pc = pc[ok]
+    u = torch.trunc(fx * pc[:, 0] / pc[:, 2] + W / 2.0).long()
+    v = torch.trunc(fy * pc[:, 1] / pc[:, 2] + H / 2.0).long()
+    inside = (u >= 0) & (u < W) & (v >= 0) & (v < H)
+    flat = (v * W + u)[inside]
+    depth = torch.full((H * W,), float("inf"), dtype=torch.float64)
+    depth.scatter_reduce_(0, flat, pc[inside, 2], reduce="amin")
+    depth = torch.where(torch.isinf(depth), torch.zeros_like(depth), depth)
+    return depth.reshape(H, W).float()
