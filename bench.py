@@ -597,7 +597,6 @@ def main():
                                            shs=params["shs"].detach(), scales=params["scales"].detach(),
                                            rotations=params["rotations"].detach(), opt=T.TouchOptions(tile_rows=band))
         I_cam0 = int(st["num_rendered"])
-        live_cam0 = int((st["ranges_live"][:, 1] - st["ranges_live"][:, 0]).long().sum())
         n_vis = int((st["radii"] > 0).sum())
         del st
 
@@ -690,7 +689,7 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.config}: {N} Gaussians, {W}x{H}, SH deg {cfg['sh_degree']}, fused touch depth-L1 "
                                f"(mult {DEPTH_LOSS_MULT}), {len(batches)} orbit cameras cycled",
-                   "num_rendered_cam0": I_cam0, "live_instances_cam0": live_cam0, "visible_cam0": n_vis,
+                   "num_rendered_cam0": I_cam0, "visible_cam0": n_vis,
                    "parallelism": "single GPU" if world == 1 else f"tile-row shard x{world}; [N,10] fp32 screen-gradient exchange: {exchange}",
                    "rendered_hint": "off (synchronous sizing)" if args.no_hints else "per-view instance count of the previous visit +5% (speculative sizing; exact re-run on overflow)",
                    "l2_policy": "working set per step (params+grads 472 MB, instance records >250 MB) exceeds the 126 MB L2; no explicit flush"},

@@ -262,11 +262,8 @@ typedef struct TgsGeomLayout {
     size_t total;
 } TgsGeomLayout;
 typedef struct TgsBinningLayout {
-    size_t ranges;            /* uint32[T,2] ranges of the full sorted list */
-    size_t ranges_live;       /* uint32[T,2] (start, start + live count) of each tile's packed live list */
-    size_t records;           /* TgsRecord[I]: per tile, the depth-sorted LIVE instances (those whose alpha >= 1/255
-                               * ellipse can reach the tile), contiguous from the tile's range start; c.w = bits of the
-                               * instance's position in the tile's full sorted list */
+    size_t ranges;            /* uint32[T,2] */
+    size_t records;           /* TgsRecord[I], depth-sorted per tile, contiguous */
     size_t tile_sorted;       /* key_bytes x [I]: tile id of every sorted instance */
     size_t vals_sorted;       /* uint32[I] Gaussian ids, final order */
     size_t tile_unsorted;     /* key_bytes x [I] (emission order: depth-major) */
@@ -280,7 +277,6 @@ typedef struct TgsImageLayout {
     size_t final_T;        /* float[H,W] */
     size_t n_contrib;      /* uint32[H,W] */
     size_t depth_raw;      /* float[H,W] un-normalised sum depth*alpha*T */
-    size_t n_contrib_live; /* uint32[H,W] last contributor as a position in the tile's packed live list */
     size_t total;
 } TgsImageLayout;
 int tgs_geom_layout(int32_t N, TgsGeomLayout* out);

@@ -65,12 +65,12 @@ class TgsGeomLayout(C.Structure):
 
 class TgsBinningLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in
-                ("ranges", "ranges_live", "records", "tile_sorted", "vals_sorted", "tile_unsorted", "vals_unsorted",
+                ("ranges", "records", "tile_sorted", "vals_sorted", "tile_unsorted", "vals_unsorted",
                  "sort_temp", "sort_temp_bytes", "key_bytes", "total")]
 
 
 class TgsImageLayout(C.Structure):
-    _fields_ = [(n, C.c_size_t) for n in ("final_T", "n_contrib", "depth_raw", "n_contrib_live", "total")]
+    _fields_ = [(n, C.c_size_t) for n in ("final_T", "n_contrib", "depth_raw", "total")]
 
 
 class TgsRefBinningLayout(C.Structure):

@@ -101,7 +101,6 @@ extern "C" int tgs_binning_layout(int64_t I, int32_t T, TgsBinningLayout* o) {
     Carver c; size_t n = (size_t)(I > 0 ? I : 0);
     o->key_bytes = T < 65535 ? 2 : 4;
     o->ranges = c.take((size_t)(T > 0 ? T : 1) * sizeof(uint2));
-    o->ranges_live = c.take((size_t)(T > 0 ? T : 1) * sizeof(uint2));
     o->records = c.take(n * sizeof(TgsRecord));
     o->tile_sorted = c.take(n * o->key_bytes);
     o->vals_sorted = c.take(n * sizeof(uint32_t));
@@ -117,7 +116,6 @@ extern "C" int tgs_image_layout(int32_t W, int32_t H, TgsImageLayout* o) {
     o->final_T = c.take(p * 4);
     o->n_contrib = c.take(p * 4);
     o->depth_raw = c.take(p * 4);
-    o->n_contrib_live = c.take(p * 4);
     o->total = c.off;
     return 0;
 }
@@ -136,7 +134,7 @@ GeomView tgs_geom_view(void* base, int N) {
 BinView tgs_bin_view(void* base, int64_t I, int T) {
     TgsBinningLayout l; tgs_binning_layout(I, T, &l);
     char* b = (char*)base; BinView v;
-    v.ranges = (uint2*)(b + l.ranges); v.ranges_live = (uint2*)(b + l.ranges_live); v.records = (TgsRecord*)(b + l.records);
+    v.ranges = (uint2*)(b + l.ranges); v.records = (TgsRecord*)(b + l.records);
     v.tile_sorted = b + l.tile_sorted; v.vals_sorted = (uint32_t*)(b + l.vals_sorted);
     v.tile_unsorted = b + l.tile_unsorted; v.vals_unsorted = (uint32_t*)(b + l.vals_unsorted);
     v.cub_temp = b + l.sort_temp; v.cub_temp_bytes = l.sort_temp_bytes;
@@ -146,7 +144,7 @@ ImageView tgs_image_view(void* base, int W, int H) {
     TgsImageLayout l; tgs_image_layout(W, H, &l);
     char* b = (char*)base; ImageView v;
     v.final_T = (float*)(b + l.final_T); v.n_contrib = (uint32_t*)(b + l.n_contrib);
-    v.depth_raw = (float*)(b + l.depth_raw); v.n_contrib_live = (uint32_t*)(b + l.n_contrib_live);
+    v.depth_raw = (float*)(b + l.depth_raw);
     return v;
 }
 

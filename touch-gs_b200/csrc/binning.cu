@@ -10,13 +10,12 @@
 //      coalesced) with the TILE ID as the only key (16 bits when T <= 65536);
 //   3. stable radix sort of I (tile, id) pairs over ceil(log2 T) bits: 2 onesweep passes on 6-byte pairs
 //      instead of 6 passes on 12-byte pairs.  Stability carries the depth order into every tile.
-//   4. tile-range detection, then per-tile packing of the sorted 48-byte records with EXACT tile-level culling:
-//      only the instances that can reach alpha >= 1/255 somewhere on their tile are written (k_pack_live).
+//   4. fused tile-range detection + packing of the sorted 48-byte records (gather -> shared memory ->
+//      one TMA bulk store per 256 records, so the packed array is written with full-line stores).
 // The scans / sorts are CUB device primitives (library code, like cuBLAS for a plain GEMM).
 // Roofline: HBM.  Algorithmic bytes per instance: key/val write 12, sort 24, range detect 8,
 // record gather 48 + write 48 (we move 6-byte pairs, so real traffic is below the algorithmic figure).
 #include "tgs_common.cuh"
-#include "render_math.cuh"
 #include <cub/cub.cuh>
 
 namespace {
@@ -65,86 +64,48 @@ k_emit(int N, const uint32_t* __restrict__ order, const uint32_t* __restrict__ t
     }
 }
 
-// A4: tile ranges of the sorted list (identifyTileRanges).
+// Fused A4 + record packing.  256 instances per CTA: each thread gathers its instance's 48-byte record
+// (3 x LDG.128, mostly L2 hits: the per-Gaussian record array is 48 MB at 1M splats) into shared memory,
+// performs the tile-boundary test of identifyTileRanges, and one thread writes the 12 KB block back with
+// a single TMA bulk store.
 template <typename KeyT>
 __global__ void __launch_bounds__(256)
-k_ranges(int64_t I_host, const uint32_t* __restrict__ I_dev, int64_t cap, const KeyT* __restrict__ keys,
-         uint2* __restrict__ ranges) {
+k_pack_ranges(int64_t I_host, const uint32_t* __restrict__ I_dev, int64_t cap, const KeyT* __restrict__ keys,
+              const uint32_t* __restrict__ vals, const float4* __restrict__ rec_in, float4* __restrict__ rec_out,
+              uint2* __restrict__ ranges) {
+    __shared__ __align__(128) float4 sm[256 * 3];
     // exact mode: I_host; speculative mode: the real count lives on the device (last scan element), clamped
     // to the buffer capacity (an overflowing speculation is discarded and re-run by the host)
     int64_t I = I_host;
     if (I_dev) { I = (int64_t)*I_dev; if (I > cap) I = cap; }
-    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (j >= I) return;
-    const uint32_t tile = (uint32_t)keys[j];
-    if (j == 0) ranges[tile].x = 0;
-    else {
-        const uint32_t prev = (uint32_t)keys[j - 1];
-        if (prev != tile) { ranges[prev].y = (uint32_t)j; ranges[tile].x = (uint32_t)j; }
+    const int64_t j0 = (int64_t)blockIdx.x * 256;
+    if (j0 >= I) return;
+    const int64_t j = j0 + threadIdx.x;
+    if (j < I) {
+        const uint32_t id = vals[j];
+        const float4* src = rec_in + (size_t)3 * id;
+        const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+        sm[3 * threadIdx.x] = a; sm[3 * threadIdx.x + 1] = b; sm[3 * threadIdx.x + 2] = c;
+        const uint32_t tile = (uint32_t)keys[j];
+        if (j == 0) ranges[tile].x = 0;
+        else {
+            const uint32_t prev = (uint32_t)keys[j - 1];
+            if (prev != tile) { ranges[prev].y = (uint32_t)j; ranges[tile].x = (uint32_t)j; }
+        }
+        if (j == I - 1) ranges[tile].y = (uint32_t)I;
     }
-    if (j == I - 1) ranges[tile].y = (uint32_t)I;
-}
-
-// Record packing WITH EXACT TILE-LEVEL CULLING.  The spec'd sorted list (keys / vals / ranges above) is built from
-// the 3-sigma bounding squares and stays untouched and inspectable; but most of its (tile, splat) instances can
-// never reach alpha >= 1/255 on any pixel of their tile (the closed-form bound of render_math.cuh::rect_may_touch,
-// here on the tile's 16x16 pixel rectangle), so they can never be blended and the compositing kernels need not see
-// them.  One CTA per tile walks the tile's range in order, gathers each instance's per-Gaussian record (L2-resident:
-// 48 MB at 1M splats), keeps the live ones, and writes them LEFT-JUSTIFIED into the tile's own slice of the packed
-// array (ordered block compaction: ballot + warp prefix), remembering each record's position in the full list
-// (c.w) so that n_contrib is still reported in the spec'd indexing.  Results are bit-identical; the packed lists,
-// their TMA staging and the per-warp cull work shrink by the live fraction.
-constexpr int kPackItems = 4;          // instances per thread per round: four independent gathers in flight
-__global__ void __launch_bounds__(256)
-k_pack_live(const uint2* __restrict__ ranges, uint2* __restrict__ ranges_live, const uint32_t* __restrict__ vals,
-            const float4* __restrict__ rec_in, float4* __restrict__ rec_out, int Tx) {
-    __shared__ uint32_t wcount[kPackItems][8];
-    const int tile = blockIdx.x;
-    const uint2 rng = ranges[tile];
-    const int len = (int)(rng.y - rng.x);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (len == 0) { if (tid == 0) ranges_live[tile] = make_uint2(rng.x, rng.x); return; }
-    const float x0 = (float)((tile % Tx) * TGS_TILE), y0 = (float)((tile / Tx) * TGS_TILE);
-    const float x1 = x0 + (float)(TGS_TILE - 1), y1 = y0 + (float)(TGS_TILE - 1);
-    uint32_t base = 0;
-    for (int c0 = 0; c0 < len; c0 += 256 * kPackItems) {
-        float4 a[kPackItems], b[kPackItems];
-        const float4* src[kPackItems];
-        unsigned m[kPackItems];
-#pragma unroll
-        for (int k = 0; k < kPackItems; ++k) {                     // list position of item k: c0 + k*256 + tid (coalesced)
-            const int j = c0 + k * 256 + tid;
-            src[k] = rec_in + (size_t)3 * (j < len ? vals[rng.x + j] : 0u);
-        }
-#pragma unroll
-        for (int k = 0; k < kPackItems; ++k)
-            if (c0 + k * 256 + tid < len) { a[k] = __ldg(src[k]); b[k] = __ldg(src[k] + 1); }
-#pragma unroll
-        for (int k = 0; k < kPackItems; ++k) {
-            const bool live = (c0 + k * 256 + tid < len) && rect_may_touch(a[k], b[k], splat_thr(b[k].w), x0, x1, y0, y1);
-            m[k] = __ballot_sync(kFull, live);
-            if (lane == 0) wcount[k][warp] = __popc(m[k]);
-        }
-        __syncthreads();
-        uint32_t run = base;
-#pragma unroll
-        for (int k = 0; k < kPackItems; ++k) {
-            uint32_t before = 0, total = 0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) { const uint32_t n = wcount[k][w]; total += n; if (w < warp) before += n; }
-            if (m[k] & (1u << lane)) {
-                const uint32_t pos = run + before + __popc(m[k] & ((1u << lane) - 1u));
-                float4* dst = rec_out + (size_t)3 * (rng.x + pos);
-                float4 c = __ldg(src[k] + 2);
-                c.w = __int_as_float(c0 + k * 256 + tid);          // position in the tile's full sorted list
-                dst[0] = a[k]; dst[1] = b[k]; dst[2] = c;
-            }
-            run += total;
-        }
-        base = run;
-        __syncthreads();
+    // make the generic-proxy shared-memory writes visible to the async proxy, then bulk-store
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int64_t n = (I - j0) < 256 ? (I - j0) : 256;
+        const uint32_t bytes = (uint32_t)n * 48u;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(rec_out + 3 * j0),
+                     "r"((uint32_t)__cvta_generic_to_shared(sm)), "r"(bytes)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released after the read
     }
-    if (tid == 0) ranges_live[tile] = make_uint2(rng.x, rng.x + base);
 }
 
 template <typename KeyT>
@@ -171,12 +132,10 @@ int emit_sort_pack(GeomView gv, BinView bv, int N, int64_t I, int64_t cap, bool 
     }
     {
         TgsProfScope prof(TGS_STAGE_PACK, st);
-        k_ranges<KeyT><<<(unsigned)((I + 255) / 256), 256, 0, st>>>(I, spec ? gv.offsets + (N - 1) : nullptr, cap, ks,
-                                                                   bv.ranges);
-        k_pack_live<<<T, 256, 0, st>>>(bv.ranges, bv.ranges_live, bv.vals_sorted,
-                                       reinterpret_cast<const float4*>(gv.records),
-                                       reinterpret_cast<float4*>(bv.records), Tx);
-        tgs_count_own(2);
+        k_pack_ranges<KeyT><<<(unsigned)((I + 255) / 256), 256, 0, st>>>(
+            I, spec ? gv.offsets + (N - 1) : nullptr, cap, ks, bv.vals_sorted,
+            reinterpret_cast<const float4*>(gv.records), reinterpret_cast<float4*>(bv.records), bv.ranges);
+        tgs_count_own(1);
         TGS_CUDA(cudaGetLastError());
     }
     return 0;
@@ -222,7 +181,7 @@ int tgs_depth_order_and_scan(GeomView gv, int N, cudaStream_t st) {
 int tgs_emit_sort_pack(GeomView gv, BinView bv, int N, int64_t count, int64_t cap, bool speculative, int T, int Tx,
                        cudaStream_t st) {
     TGS_CUDA(cudaMemsetAsync(bv.ranges, 0, sizeof(uint2) * (size_t)T, st));
-    if (count == 0 || N == 0) { TGS_CUDA(cudaMemsetAsync(bv.ranges_live, 0, sizeof(uint2) * (size_t)T, st)); return 0; }
+    if (count == 0 || N == 0) return 0;
     int bits = 1;
     while ((1 << bits) < T) ++bits;
     if (speculative && (1 << bits) == T) ++bits;     // the all-ones pad key must compare above every tile id

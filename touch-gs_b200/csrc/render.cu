@@ -85,8 +85,40 @@ __device__ __forceinline__ PixelMap map_pixel(int tile, int Tx, int W, int H) {
     return m;
 }
 
-__device__ __forceinline__ bool patch_may_touch(const float4 a, const float4 q, const PixelMap& pm) {
-    return rect_may_touch(a, q, splat_thr(q.w), pm.x0, pm.x1, pm.y0, pm.y1);
+// EXACT warp-level cull.  A splat can only contribute to a pixel if alpha = o*exp(power) >= 1/255,
+// i.e. power >= thr := -ln(255 o)  (thr is precomputed per splat in record.c.w).  power = -q/2 with
+// q(p) = (p-mu)^T Q (p-mu) convex, so over the warp's pixel rectangle R the maximum power is -q_min/2
+// where q_min is 0 if mu lies in R and otherwise the minimum over the four edges (each a clamped 1-D
+// quadratic).  If even that maximum is below thr (minus a safety margin that dominates the fp32
+// rounding of this bound and of the per-pixel evaluation), NO pixel of the patch would pass the
+// alpha test, so skipping the splat for the whole warp is bit-identical to evaluating it.
+__device__ __forceinline__ bool patch_may_touch(const float4 a, const float4 q, float thr, const PixelMap& pm) {
+    const float ex0 = pm.x0 - a.x, ex1 = pm.x1 - a.x, ey0 = pm.y0 - a.y, ey1 = pm.y1 - a.y;
+    if (ex0 <= 0.0f && ex1 >= 0.0f && ey0 <= 0.0f && ey1 >= 0.0f) return thr <= 0.05f;
+    const float A = q.x, B = q.y, Cc = q.z;
+    const float rA = __fdividef(1.0f, A), rC = __fdividef(1.0f, Cc);
+    float qmin, tmax;
+    {   // vertical edges: dx fixed, dy* = clamp(-B dx / C)
+        float dy = fminf(fmaxf(-B * ex0 * rC, ey0), ey1);
+        float t1 = A * ex0 * ex0, t2 = Cc * dy * dy, t3 = 2.0f * B * ex0 * dy;
+        qmin = t1 + t2 + t3; tmax = t1 + t2 + fabsf(t3);
+        dy = fminf(fmaxf(-B * ex1 * rC, ey0), ey1);
+        t1 = A * ex1 * ex1; t2 = Cc * dy * dy; t3 = 2.0f * B * ex1 * dy;
+        float qq = t1 + t2 + t3;
+        if (qq < qmin) { qmin = qq; tmax = t1 + t2 + fabsf(t3); }
+    }
+    {   // horizontal edges: dy fixed, dx* = clamp(-B dy / A)
+        float dx = fminf(fmaxf(-B * ey0 * rA, ex0), ex1);
+        float t1 = A * dx * dx, t2 = Cc * ey0 * ey0, t3 = 2.0f * B * dx * ey0;
+        float qq = t1 + t2 + t3;
+        if (qq < qmin) { qmin = qq; tmax = t1 + t2 + fabsf(t3); }
+        dx = fminf(fmaxf(-B * ey1 * rA, ex0), ex1);
+        t1 = A * dx * dx; t2 = Cc * ey1 * ey1; t3 = 2.0f * B * dx * ey1;
+        qq = t1 + t2 + t3;
+        if (qq < qmin) { qmin = qq; tmax = t1 + t2 + fabsf(t3); }
+    }
+    const float margin = 0.05f + 1e-5f * tmax;
+    return -0.5f * qmin >= thr - margin;
 }
 
 // ------------------------------------------------------------------------------- forward
@@ -94,7 +126,7 @@ __global__ void __launch_bounds__(256)
 k_render_fwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ recs, int W, int H, int Tx,
              int row0, const float* __restrict__ bg, int normalize, float* __restrict__ out_color,
              float* __restrict__ out_depth, float* __restrict__ out_alpha, float* __restrict__ final_T,
-             uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ n_contrib_live, float* __restrict__ depth_raw,
+             uint32_t* __restrict__ n_contrib, float* __restrict__ depth_raw,
              const float* __restrict__ t_target, float* __restrict__ residual) {
     __shared__ __align__(128) float4 sbuf[2][kBatch * 3];
     __shared__ __align__(8) uint64_t full[2];
@@ -116,7 +148,7 @@ k_render_fwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
     if (tid == 0) { if (nb > 0) issue(0); if (nb > 1) issue(1); }
 
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
-    uint32_t last = 0, last_live = 0;      // last contributor: position in the spec'd sorted list / in the live list
+    uint32_t last = 0;
     bool done = !pm.inside;
     int b = 0;
     for (; b < nb; ++b) {
@@ -127,7 +159,7 @@ k_render_fwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
             if (__all_sync(kFull, done)) break;                 // whole warp saturated
             const int jl = c0 + lane;
             bool pass = false;
-            if (jl < cnt) pass = patch_may_touch(s[3 * jl], s[3 * jl + 1], pm);
+            if (jl < cnt) pass = patch_may_touch(s[3 * jl], s[3 * jl + 1], s[3 * jl + 2].w, pm);
             unsigned mask = __ballot_sync(kFull, pass);
             while (mask) {
                 const int j = c0 + __ffs(mask) - 1;
@@ -145,8 +177,7 @@ k_render_fwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
                     const float w = alpha * T;
                     C0 += c.x * w; C1 += c.y * w; C2 += c.z * w; D += a.z * w;
                     T = test_T;
-                    last = (uint32_t)__float_as_int(c.w) + 1u;       // c.w = position in the tile's FULL sorted list
-                    last_live = (uint32_t)(b * kBatch + j + 1);
+                    last = (uint32_t)(b * kBatch + j + 1);
                 }
             }
         }
@@ -173,7 +204,6 @@ k_render_fwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
         }
         final_T[pm.pix] = T;
         n_contrib[pm.pix] = last;
-        n_contrib_live[pm.pix] = last_live;
         depth_raw[pm.pix] = D;
     }
 }
@@ -318,7 +348,7 @@ k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
         for (int c0 = ((cnt - 1) >> 5) << 5; c0 >= 0; c0 -= 32) {
             const int jl = c0 + lane;
             bool pass = false;
-            if (jl < cnt) pass = patch_may_touch(s[3 * jl], s[3 * jl + 1], pm);
+            if (jl < cnt) pass = patch_may_touch(s[3 * jl], s[3 * jl + 1], s[3 * jl + 2].w, pm);
             unsigned mask = __ballot_sync(kFull, pass);
             while (mask) {
                 const int hb = 31 - __clz(mask);
@@ -411,9 +441,9 @@ int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, BinView bv, I
     int nt = cam.Tx * (cam.row1 - cam.row0);
     if (nt <= 0) return 0;
     TgsProfScope prof(TGS_STAGE_RENDER_FWD, st);
-    k_render_fwd<<<nt, 256, 0, st>>>(bv.ranges_live, bv.records, cam.W, cam.H, cam.Tx, cam.row0, s->bg,
+    k_render_fwd<<<nt, 256, 0, st>>>(bv.ranges, bv.records, cam.W, cam.H, cam.Tx, cam.row0, s->bg,
                                      s->depth_normalize, out_color, out_depth, out_alpha, iv.final_T,
-                                     iv.n_contrib, iv.n_contrib_live, iv.depth_raw, touch_target, residual_out);
+                                     iv.n_contrib, iv.depth_raw, touch_target, residual_out);
     tgs_count_own(1);
     TGS_KERNEL_CHECK(st, s->debug);
     return 0;
@@ -432,8 +462,8 @@ int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, BinView bv, I
         if (mode != TGS_LOSS_NONE && ts == nullptr) { tgs_set_error("touch loss enabled but scale pointer is NULL"); return TGS_EINVAL; }
     }
     TgsProfScope prof(TGS_STAGE_RENDER_BWD, st);
-    k_render_bwd<<<2 * nt, kBwdThreads, 0, st>>>(bv.ranges_live, bv.records, cam.W, cam.H, cam.Tx, cam.row0, s->bg,
-                                     s->depth_normalize, iv.final_T, iv.n_contrib_live, iv.depth_raw, dL_dcolor,
+    k_render_bwd<<<2 * nt, kBwdThreads, 0, st>>>(bv.ranges, bv.records, cam.W, cam.H, cam.Tx, cam.row0, s->bg,
+                                     s->depth_normalize, iv.final_T, iv.n_contrib, iv.depth_raw, dL_dcolor,
                                      dL_ddepth, dL_dalpha, tt, tw, ts, mode, tr0, tr1, residual, screen_grads);
     tgs_count_own(1);
     TGS_KERNEL_CHECK(st, s->debug);

@@ -13,9 +13,7 @@
 // into shared memory by a single TMA bulk copy (cp.async.bulk) per batch.
 //   a = (x_pix, y_pix, depth, bits(gaussian id))
 //   b = (conic A, conic B, conic C, opacity)
-//   c = (r, g, b, w)     per-Gaussian record: w = thr = -ln(255*opacity), the power threshold of the alpha >= 1/255
-//                        test; per-instance record: w = bits(position in the tile's FULL sorted list), because
-//                        the packed per-tile lists hold only the LIVE instances (see binning.cu::k_pack_live)
+//   c = (r, g, b, thr)   thr = -ln(255*opacity): power threshold of the alpha >= 1/255 test
 struct __align__(16) TgsRecord { float4 a, b, c; };
 static_assert(sizeof(TgsRecord) == 48, "record must be 48 bytes");
 
@@ -65,14 +63,12 @@ struct GeomView {
 struct BinView {
     void* tile_unsorted; uint32_t* vals_unsorted;   // tile ids are uint16 when T <= 65536, else uint32
     void* tile_sorted;   uint32_t* vals_sorted;
-    uint2* ranges;           // [T] the spec'd ranges of the full sorted list (A4)
-    uint2* ranges_live;      // [T] (start, start + live count): the packed LIVE list of each tile, left-justified
-    TgsRecord* records;      // [I] packed, sorted, live instances only
+    uint2* ranges;           // [T]
+    TgsRecord* records;      // [I] packed, sorted
     void* cub_temp; size_t cub_temp_bytes;
 };
 struct ImageView {
     float* final_T; uint32_t* n_contrib; float* depth_raw;
-    uint32_t* n_contrib_live;   // last contributor as a position in the LIVE list (what backward replays)
 };
 GeomView tgs_geom_view(void* base, int N);
 BinView tgs_bin_view(void* base, int64_t I, int T);

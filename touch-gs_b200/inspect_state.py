@@ -72,21 +72,11 @@ def forward_state(means3D, opacities, rs: GaussianRasterizationSettings, shs=Non
         vals_emitted=_view(binning, bl.vals_unsorted, I, torch.int32),
         vals=_view(binning, bl.vals_sorted, I, torch.int32),
         ranges=_view(binning, bl.ranges, Tx * Ty * 2, torch.int32).view(Tx * Ty, 2),
-        ranges_live=_view(binning, bl.ranges_live, Tx * Ty * 2, torch.int32).view(Tx * Ty, 2),
         records=_view(binning, bl.records, I * 12, torch.float32).view(I, 12),
         final_T=_view(image, il.final_T, H * W, torch.float32).view(H, W),
         n_contrib=_view(image, il.n_contrib, H * W, torch.int32).view(H, W),
         depth_raw=_view(image, il.depth_raw, H * W, torch.float32).view(H, W),
-        n_contrib_live=_view(image, il.n_contrib_live, H * W, torch.int32).view(H, W),
     )
-    # positions (in the packed record array) of the LIVE instances of every tile, and for each its position in the
-    # full sorted list: the packed per-tile lists hold only instances that can reach alpha >= 1/255 on their tile
-    rl = out["ranges_live"].long()
-    cnt = rl[:, 1] - rl[:, 0]
-    tile_of = torch.repeat_interleave(torch.arange(rl.shape[0], device=rl.device), cnt)
-    first = torch.cumsum(cnt, 0) - cnt
-    out["live_pos"] = rl[tile_of, 0] + (torch.arange(int(cnt.sum()), device=rl.device) - first[tile_of])
-    out["live_full_pos"] = rl[tile_of, 0] + out["records"][out["live_pos"], 11].contiguous().view(torch.int32).long()
     # the spec'd 64-bit sort key of every sorted instance: tile << 32 | bits(depth of its Gaussian)
     dbits = out["gdepth"].contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
     out["keys"] = (out["tile_ids"] << 32) | dbits[out["vals"].long()]
