@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TGS_ABI_VERSION 2
+#define TGS_ABI_VERSION 3
 
 #define TGS_EINVAL   (-1)   /* bad argument combination / shape */
 #define TGS_ENOMEM   (-2)   /* allocator callback returned NULL */
@@ -74,6 +74,11 @@ typedef struct TgsSettings {
     const float* projmatrix;  /* [16] device */
     const float* campos;      /* [3]  device */
     const float* bg;          /* [3]  device */
+    /* convention switches; 0 = the primary (Inria) convention */
+    float   alpha_max;        /* alpha clamp: 0 -> 0.99;  gsplat 0.1.x: 0.999 */
+    float   near_z;           /* near-plane cull, view z <= near_z: 0 -> 0.2;  gsplat 0.1.x clip_thresh: 0.01 */
+    float   principal_dx;     /* principal point offset from the image centre in pixels (cx - W/2, cy - H/2): added to */
+    float   principal_dy;     /* the pixel mean after the NDC -> pixel map (gsplat 0.1.x ndc2pix(x, W, cx)) */
 } TgsSettings;
 
 /* Per-Gaussian inputs (replaces the tensor arguments of rasterize_gaussians). */
@@ -389,6 +394,38 @@ int tgs_densify_plan(int32_t N, const float* opacity_logit, const float* scales_
 int tgs_densify_apply(int32_t N, int32_t K, const uint32_t* counts, const uint32_t* offsets, const float* noise,
                       const TgsDensifyConfig* cfg, const TgsParamSet* in_pmv, const TgsParamSet* out_pmv,
                       int32_t* src_out, void* stream);
+
+/* ====================================================================================================
+ * SURVEY.md §8(f) row N3 -- the hot path split at the screen-space boundary, as the gsplat-0.1-style three-call API
+ * of the nerfstudio splat model the Touch-GS fork builds on expects it (reference .gitmodules:7-9 -> empty submodule;
+ * trainer entry reference scripts/train_bunny_real.sh:52): project_gaussians -> caller's colours -> rasterize_gaussians.
+ * Same kernels as the fused path; convention differences are the TgsSettings switches alpha_max / near_z /
+ * principal_dx,dy and the pixel_offset argument.
+ * ==================================================================================================== */
+/* A1 alone (geometry only: shs / colors_precomp / opacities of `g` are ignored).  Results live in saved->geom
+ * (layout: tgs_geom_layout): records (x, y, depth | conic A,B,C), cov3D, tiles_touched; radii [N] is written. */
+int tgs_project_gaussians(const TgsSettings* s, const TgsGaussians* g, tgs_alloc_fn alloc, void* alloc_user,
+                          int32_t* radii, TgsSaved* saved, void* stream);
+/* chain rule of the projection: screen_grads [N,10] (slots 0,1 = d/dxy in pixels, 2..4 = d/dconic, 9 = d/ddepth; the
+ * others are ignored) -> grads->dmeans3D, dscales, drotations (or dcov3D), dmeans2D. */
+int tgs_project_gaussians_backward(const TgsSettings* s, const TgsGaussians* g, const TgsSaved* saved,
+                                   const int32_t* radii, const float* screen_grads, const TgsGrads* grads, void* stream);
+/* A2-A5 from caller-provided screen-space tensors: xys [N,2] pixels, depths [N], radii [N] (<= 0: skipped),
+ * conics [N,3], colors [N,3], opacities [N].  Sample point of pixel (x,y) = (x + pixel_offset, y + pixel_offset).
+ * out_color [3,H,W] (incl. background), out_depth [H,W] = sum depth*alpha*T, out_alpha [H,W].
+ * Only image_width / image_height / bg / alpha_max / tile rows of `s` are used. */
+int tgs_rasterize_screen_forward(const TgsSettings* s, int32_t N, const float* xys, const float* depths,
+                                 const int32_t* radii, const float* conics, const float* colors,
+                                 const float* opacities, float pixel_offset, tgs_alloc_fn alloc, void* alloc_user,
+                                 float* out_color, float* out_depth, float* out_alpha, TgsSaved* saved, void* stream);
+/* A6 without the touch fusion: screen_grads [N,10] = (dxy pixels, dconic, dopacity, dcolor, ddepth) */
+int tgs_rasterize_screen_backward(const TgsSettings* s, int32_t N, const TgsSaved* saved, const float* dL_dcolor,
+                                  const float* dL_ddepth, const float* dL_dalpha, float* screen_grads, void* stream);
+/* colours [N,3] = sum_k Y_k(dir/|dir|) coeffs[N,K,3] over the (degree+1)^2 active bases, RAW (no +0.5, no clamp) */
+int tgs_spherical_harmonics(int32_t N, int32_t degree, int32_t K, const float* dirs, const float* coeffs,
+                            float* colors, void* stream);
+int tgs_spherical_harmonics_backward(int32_t N, int32_t degree, int32_t K, const float* dirs, const float* v_colors,
+                                     float* v_coeffs, void* stream);
 
 #ifdef __cplusplus
 }

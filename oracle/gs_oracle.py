@@ -78,6 +78,11 @@ class OracleSettings(NamedTuple):
     campos: torch.Tensor        # [3]
     prefiltered: bool = False
     debug: bool = False
+    # convention switches; the defaults are the primary (Inria) convention
+    alpha_max: float = ALPHA_MAX          # gsplat 0.1.x: 0.999
+    near_z: float = NEAR_Z                # gsplat 0.1.x clip_thresh: 0.01
+    principal: tuple = (0.0, 0.0)         # (cx - W/2, cy - H/2) in pixels
+    pixel_offset: float = 0.0             # sample point (x + offset, y + offset); later gsplat 0.1.x: 0.5
 
 
 def camera_scalars(S, dtype=torch.float32):
@@ -164,11 +169,11 @@ def preprocess(means3D, scales, rotations, opacities, shs, colors_precomp,
     x, y, z = means3D.unbind(-1)
     tx, ty, tz = (_xform(vm, x, y, z, c) for c in range(3))
     hx, hy, hw = _xform(pm, x, y, z, 0), _xform(pm, x, y, z, 1), _xform(pm, x, y, z, 3)
-    vis = tz > NEAR_Z
+    vis = tz > S.near_z
     pw = 1.0 / (hw + 1e-7)
     ndcx, ndcy = hx * pw, hy * pw
-    px = ((ndcx + 1.0) * W - 1.0) * 0.5
-    py = ((ndcy + 1.0) * H - 1.0) * 0.5
+    px = ((ndcx + 1.0) * W - 1.0) * 0.5 + float(np.float32(S.principal[0]))
+    py = ((ndcy + 1.0) * H - 1.0) * 0.5 + float(np.float32(S.principal[1]))
 
     # --- 3D covariance
     if cov3D_precomp is not None:
@@ -320,7 +325,7 @@ def _fov_clamp(t, tz, lim):
     return torch.where(inside, t + (val - t).detach(), val.detach())
 
 
-def _composite_tile(xy, conic, opac, rgb, depth, pix):
+def _composite_tile(xy, conic, opac, rgb, depth, pix, alpha_max=ALPHA_MAX):
     """Appendix A.1: vectorised front-to-back compositing reproducing sequential early exit.
 
     xy [L,2], conic [L,3], opac [L], rgb [L,3], depth [L]; pix [P,2] float pixel coords."""
@@ -328,7 +333,7 @@ def _composite_tile(xy, conic, opac, rgb, depth, pix):
     dy = xy[None, :, 1] - pix[:, None, 1]
     A, B, C = conic[None, :, 0], conic[None, :, 1], conic[None, :, 2]
     power = -0.5 * (A * dx * dx + C * dy * dy) - B * dx * dy
-    alpha = _st_clamp_max(opac[None, :] * torch.exp(power), ALPHA_MAX)
+    alpha = _st_clamp_max(opac[None, :] * torch.exp(power), alpha_max)
     skip = (power > 0) | (alpha < ALPHA_MIN)
     a_eff = torch.where(skip, torch.zeros_like(alpha), alpha)
     one_m = 1.0 - a_eff
@@ -371,10 +376,10 @@ def render_tiles(pre: Pre, bins: Bins, S: OracleSettings, tiles=None) -> Img:
         x0, y0 = tx_ * TILE, ty_ * TILE
         x1, y1 = min(x0 + TILE, W), min(y0 + TILE, H)
         ys, xs = torch.meshgrid(torch.arange(y0, y1), torch.arange(x0, x1), indexing="ij")
-        pix = torch.stack([xs.reshape(-1), ys.reshape(-1)], -1).to(dt)
+        pix = torch.stack([xs.reshape(-1), ys.reshape(-1)], -1).to(dt) + S.pixel_offset
         g = vals[lo:hi]
         col, dep, ft, nc = _composite_tile(pre.xy[g], pre.conic[g], pre.opacity[g],
-                                           pre.rgb[g], pre.depth[g], pix)
+                                           pre.rgb[g], pre.depth[g], pix, S.alpha_max)
         hh, ww = y1 - y0, x1 - x0
         color[:, y0:y1, x0:x1] = (col + ft[:, None] * bg[None, :]).t().reshape(3, hh, ww)
         depth[y0:y1, x0:x1] = dep.reshape(hh, ww)

@@ -12,7 +12,8 @@ from helpers import O, synth, oracle_settings
 
 class Cam(ctypes.Structure):
     _fields_ = [(n, ctypes.c_float) for n in ("fx", "fy", "limx", "limy", "mod")] + \
-               [(n, ctypes.c_int) for n in ("W", "H", "Tx", "Ty", "row0", "row1", "deg", "K")]
+               [(n, ctypes.c_int) for n in ("W", "H", "Tx", "Ty", "row0", "row1", "deg", "K")] + \
+               [(n, ctypes.c_float) for n in ("near_z", "ppx", "ppy", "alpha_max")]
 
 
 def P(a):
@@ -40,7 +41,7 @@ def test_forward_bit_exact_and_backward(host_math_lib, case):
     Tx, Ty = (W + 15) // 16, (H + 15) // 16
     b = band or (0, Ty)
     K = (deg + 1) ** 2
-    c = Cam(fx, fy, lx, ly, mod, W, H, Tx, Ty, b[0], b[1], deg, K)
+    c = Cam(fx, fy, lx, ly, mod, W, H, Tx, Ty, b[0], b[1], deg, K, 0.2, 0.0, 0.0, 0.99)
     ins = [t.clone().requires_grad_(True) for t in (sc.means3D, sc.scales, sc.rotations, sc.opacities, sc.shs)]
     m, s, r, o, sh = ins
     pre = O.preprocess(m, s, r, o, sh, None, None, S, band)
@@ -100,7 +101,7 @@ def test_precomputed_cov3d_path(host_math_lib):
     pre = O.preprocess(m, None, None, sc.opacities, sc.shs, None, cov_in, S)
     assert torch.equal(pre.radii, pre0.radii)
     fx, fy, lx, ly = O.camera_scalars(S)
-    c = Cam(fx, fy, lx, ly, 1.0, W, H, 6, 4, 0, 4, deg, 1)
+    c = Cam(fx, fy, lx, ly, 1.0, W, H, 6, 4, 0, 4, deg, 1, 0.2, 0.0, 0.0, 0.99)
     g = torch.Generator().manual_seed(1)
     vis = pre.radii.numpy() > 0
     sg = torch.randn(N, 10, generator=g) * torch.tensor(vis)[:, None]

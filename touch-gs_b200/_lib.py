@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TGS_LIB_PATH") or os.path.join(HERE, "libtgs.so")   # override: A/B builds
 
-TGS_ABI_VERSION = 2
+TGS_ABI_VERSION = 3
 BUF_GEOM, BUF_BINNING, BUF_IMAGE, BUF_TEMP = 0, 1, 2, 3
 LOSS_NONE, LOSS_L1, LOSS_L2 = 0, 1, 2
 LOSS_MODES = {"none": LOSS_NONE, "l1": LOSS_L1, "l2": LOSS_L2}
@@ -29,6 +29,7 @@ class TgsSettings(C.Structure):
         ("tile_row_begin", C.c_int32), ("tile_row_end", C.c_int32),
         ("depth_normalize", C.c_int32), ("reserved0", C.c_int32), ("rendered_hint", C.c_int64),
         ("viewmatrix", c_fp), ("projmatrix", c_fp), ("campos", c_fp), ("bg", c_fp),
+        ("alpha_max", C.c_float), ("near_z", C.c_float), ("principal_dx", C.c_float), ("principal_dy", C.c_float),
     ]
 
 
@@ -139,6 +140,16 @@ SIGNATURES = {
                                    c_fp, c_fp, c_fp, C.c_size_t, C.POINTER(C.c_int64), c_fp]),
     "tgs_densify_apply": (C.c_int, [C.c_int32, C.c_int32, c_fp, c_fp, c_fp, C.POINTER(TgsDensifyConfig),
                                     C.POINTER(TgsParamSet), C.POINTER(TgsParamSet), c_fp, c_fp]),
+    "tgs_project_gaussians": (C.c_int, [C.POINTER(TgsSettings), C.POINTER(TgsGaussians), ALLOC_FN, C.c_void_p, c_fp,
+                                        C.POINTER(TgsSaved), c_fp]),
+    "tgs_project_gaussians_backward": (C.c_int, [C.POINTER(TgsSettings), C.POINTER(TgsGaussians), C.POINTER(TgsSaved),
+                                                 c_fp, c_fp, C.POINTER(TgsGrads), c_fp]),
+    "tgs_rasterize_screen_forward": (C.c_int, [C.POINTER(TgsSettings), C.c_int32, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp,
+                                               C.c_float, ALLOC_FN, C.c_void_p, c_fp, c_fp, c_fp, C.POINTER(TgsSaved), c_fp]),
+    "tgs_rasterize_screen_backward": (C.c_int, [C.POINTER(TgsSettings), C.c_int32, C.POINTER(TgsSaved), c_fp, c_fp, c_fp,
+                                                c_fp, c_fp]),
+    "tgs_spherical_harmonics": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, c_fp, c_fp, c_fp, c_fp]),
+    "tgs_spherical_harmonics_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, c_fp, c_fp, c_fp, c_fp]),
     "tgs_refstructure_binning_layout": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.POINTER(TgsRefBinningLayout)]),
     "tgs_refstructure_forward": (C.c_int, [C.POINTER(TgsSettings), C.POINTER(TgsGaussians), ALLOC_FN, C.c_void_p,
                                            c_fp, c_fp, c_fp, c_fp, C.POINTER(TgsSaved), c_fp]),

@@ -27,6 +27,7 @@ UNITS = {
     "render.cu": [],
     "refstructure.cu": [],
     "train_ops.cu": [],
+    "screen_api.cu": [],
     "api.cu": [],
     "host_step.cu": [],
     "touch_inputs.cu": ["--fmad=false"],

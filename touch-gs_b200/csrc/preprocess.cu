@@ -79,15 +79,16 @@ k_preprocess(int N, const float* __restrict__ means, const float* __restrict__ s
                     if (k < 3 * nb) sh[k] = __ldg(src + k);
             }
             tgs_sh_forward(cam.deg, sh, x - cm.cp[0], y - cm.cp[1], z - cm.cp[2], rgb, cl);
-        } else {
+        } else if (colors) {                  // (neither: geometry-only projection, tgs_project_gaussians)
             rgb[0] = colors[3 * i]; rgb[1] = colors[3 * i + 1]; rgb[2] = colors[3 * i + 2];
         }
     }
+    const float o = opac ? opac[i] : 1.0f;
     TgsRecord r;
     r.a = make_float4(p.px, p.py, p.depth, __int_as_float(i));
-    r.b = make_float4(p.conA, p.conB, p.conC, vis ? opac[i] : 0.0f);
+    r.b = make_float4(p.conA, p.conB, p.conC, vis ? o : 0.0f);
     // c.w = power threshold of the alpha >= 1/255 test: o*exp(power) >= 1/255  <=>  power >= -ln(255 o)
-    r.c = make_float4(rgb[0], rgb[1], rgb[2], vis ? -logf(255.0f * opac[i]) : 3.0e38f);
+    r.c = make_float4(rgb[0], rgb[1], rgb[2], vis ? -logf(255.0f * o) : 3.0e38f);
     rec[i] = r;
 #pragma unroll
     for (int k = 0; k < 6; ++k) cov3D[6 * i + k] = cov[k];
@@ -187,7 +188,7 @@ k_preprocess_bwd(int N, PeerGather pg, const TgsRecord* __restrict__ rec, const 
 }
 
 __global__ void k_mark_visible(int N, const float* __restrict__ means, const float* __restrict__ vm,
-                               uint8_t* __restrict__ present) {
+                               uint8_t* __restrict__ present) {   // markVisible is an Inria-convention entry point: 0.2
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     float tz = tgs_xform(vm, means[3 * i], means[3 * i + 1], means[3 * i + 2], 2);

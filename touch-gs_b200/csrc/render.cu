@@ -124,7 +124,7 @@ __device__ __forceinline__ bool patch_may_touch(const float4 a, const float4 q, 
 // ------------------------------------------------------------------------------- forward
 __global__ void __launch_bounds__(256)
 k_render_fwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ recs, int W, int H, int Tx,
-             int row0, const float* __restrict__ bg, int normalize, float* __restrict__ out_color,
+             int row0, const float* __restrict__ bg, int normalize, float alpha_max, float* __restrict__ out_color,
              float* __restrict__ out_depth, float* __restrict__ out_alpha, float* __restrict__ final_T,
              uint32_t* __restrict__ n_contrib, float* __restrict__ depth_raw,
              const float* __restrict__ t_target, float* __restrict__ residual) {
@@ -167,7 +167,7 @@ k_render_fwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
                 const float4 a = s[3 * j], q = s[3 * j + 1];
                 const float dx = a.x - pm.fx, dy = a.y - pm.fy;
                 const float power = splat_power(q, dx, dy);
-                const float alpha = splat_alpha(q.w, splat_exp(power));
+                const float alpha = splat_alpha(q.w, splat_exp(power), alpha_max);
                 bool valid = !done && (power <= 0.0f) && (alpha >= TGS_ALPHA_MIN);
                 if (!__any_sync(kFull, valid)) continue;
                 const float test_T = T * (1.0f - alpha);
@@ -250,7 +250,7 @@ constexpr int kPix = 4;
 
 __global__ void __launch_bounds__(kBwdThreads)
 k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ recs, int W, int H, int Tx,
-             int row0, const float* __restrict__ bg, int normalize, const float* __restrict__ final_T,
+             int row0, const float* __restrict__ bg, int normalize, float alpha_max, const float* __restrict__ final_T,
              const uint32_t* __restrict__ n_contrib, const float* __restrict__ depth_raw,
              const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
              const float* __restrict__ dL_dalpha, const float* __restrict__ t_target,
@@ -379,7 +379,7 @@ k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
                 for (int r = 0; r < kPix; ++r) {
                     // pixels that do not blend this splat run with og == 0: alpha == 0, inv == 1, T untouched,
                     // u == 0 and w == 0, so every gradient term is exactly 0 without any branch
-                    const float am = fminf(TGS_ALPHA_MAX, og[r]);
+                    const float am = fminf(alpha_max, og[r]);
                     const float inv = fast_rcp(1.0f - am);
                     T[r] *= inv;                               // transmittance in front of this splat
                     const float w = am * T[r];
@@ -442,7 +442,7 @@ int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, BinView bv, I
     if (nt <= 0) return 0;
     TgsProfScope prof(TGS_STAGE_RENDER_FWD, st);
     k_render_fwd<<<nt, 256, 0, st>>>(bv.ranges, bv.records, cam.W, cam.H, cam.Tx, cam.row0, s->bg,
-                                     s->depth_normalize, out_color, out_depth, out_alpha, iv.final_T,
+                                     s->depth_normalize, cam.alpha_max, out_color, out_depth, out_alpha, iv.final_T,
                                      iv.n_contrib, iv.depth_raw, touch_target, residual_out);
     tgs_count_own(1);
     TGS_KERNEL_CHECK(st, s->debug);
@@ -463,7 +463,7 @@ int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, BinView bv, I
     }
     TgsProfScope prof(TGS_STAGE_RENDER_BWD, st);
     k_render_bwd<<<2 * nt, kBwdThreads, 0, st>>>(bv.ranges, bv.records, cam.W, cam.H, cam.Tx, cam.row0, s->bg,
-                                     s->depth_normalize, iv.final_T, iv.n_contrib, iv.depth_raw, dL_dcolor,
+                                     s->depth_normalize, cam.alpha_max, iv.final_T, iv.n_contrib, iv.depth_raw, dL_dcolor,
                                      dL_ddepth, dL_dalpha, tt, tw, ts, mode, tr0, tr1, residual, screen_grads);
     tgs_count_own(1);
     TGS_KERNEL_CHECK(st, s->debug);

@@ -14,8 +14,8 @@ static __device__ __forceinline__ float splat_power(const float4 q, float dx, fl
     const float bxy = __fmul_rn(__fmul_rn(q.y, dx), dy);
     return __fmaf_rn(-0.5f, s, -bxy);
 }
-static __device__ __forceinline__ float splat_alpha(float opacity, float G) {
-    return fminf(TGS_ALPHA_MAX, __fmul_rn(opacity, G));
+static __device__ __forceinline__ float splat_alpha(float opacity, float G, float alpha_max = TGS_ALPHA_MAX) {
+    return fminf(alpha_max, __fmul_rn(opacity, G));
 }
 // exp(power) = ex2(power*log2e) with flush-to-zero: one FMUL + one MUFU.EX2, no denormal fix-up code.
 // (power <= 0 here; results below 2^-126 flush to 0, far under the 1/255 alpha threshold.)

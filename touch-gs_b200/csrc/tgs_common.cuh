@@ -114,5 +114,8 @@ static inline TgsCam tgs_make_cam(const TgsSettings* s) {
     if (c.row0 < 0) c.row0 = 0;
     if (c.row1 > c.Ty) c.row1 = c.Ty;
     c.deg = s->sh_degree; c.K = s->sh_coeffs;
+    c.near_z = s->near_z > 0.0f ? s->near_z : TGS_NEAR_Z;
+    c.alpha_max = s->alpha_max > 0.0f ? s->alpha_max : TGS_ALPHA_MAX;
+    c.ppx = s->principal_dx; c.ppy = s->principal_dy;
     return c;
 }

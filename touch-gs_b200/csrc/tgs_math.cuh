@@ -45,6 +45,9 @@ struct TgsCam {
     float mod;
     int W, H, Tx, Ty, row0, row1;
     int deg, K;
+    float near_z;          // near-plane cull threshold (TGS_NEAR_Z unless the caller overrides it)
+    float ppx, ppy;        // principal point offset from the image centre, pixels
+    float alpha_max;       // alpha clamp (TGS_ALPHA_MAX unless the caller overrides it)
 };
 
 // ((m[0][col]*x + m[1][col]*y) + m[2][col]*z) + m[3][col], m = transposed 4x4 (row-major [k][j])
@@ -131,7 +134,7 @@ TGS_HD bool tgs_project(const float* vm, const float* pm, const TgsCam& cam,
     o.radius = 0; o.tiles = 0; o.rminx = o.rminy = o.rmaxx = o.rmaxy = 0;
     o.px = o.py = o.depth = 0.0f; o.conA = o.conB = o.conC = 0.0f;
     float tz = tgs_xform(vm, x, y, z, 2);
-    if (!(tz > TGS_NEAR_Z)) return false;
+    if (!(tz > cam.near_z)) return false;
     float tx = tgs_xform(vm, x, y, z, 0), ty = tgs_xform(vm, x, y, z, 1);
     float hx = tgs_xform(pm, x, y, z, 0), hy = tgs_xform(pm, x, y, z, 1), hw = tgs_xform(pm, x, y, z, 3);
     float pw = 1.0f / (hw + 0.0000001f);
@@ -145,8 +148,8 @@ TGS_HD bool tgs_project(const float* vm, const float* pm, const TgsCam& cam,
     float disc = sqrtf(fmaxf(mid * mid - det, 0.1f));
     float lam = fmaxf(mid + disc, mid - disc);
     float rad = ceilf(3.0f * sqrtf(fmaxf(lam, 0.0f)));
-    float px = ((ndcx + 1.0f) * (float)cam.W - 1.0f) * 0.5f;
-    float py = ((ndcy + 1.0f) * (float)cam.H - 1.0f) * 0.5f;
+    float px = ((ndcx + 1.0f) * (float)cam.W - 1.0f) * 0.5f + cam.ppx;
+    float py = ((ndcy + 1.0f) * (float)cam.H - 1.0f) * 0.5f + cam.ppy;
     int x0, x1, y0, y1;
     tgs_rect1(px, rad, cam.Tx, x0, x1);
     tgs_rect1(py, rad, cam.Ty, y0, y1);
