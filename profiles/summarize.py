@@ -46,6 +46,31 @@ if os.path.exists(path):
         w(f"| `{n}` | {c} | {t:.1f} | {100 * t / tot:.1f}% |")
     w()
 
+# ---- launch list of the train step (optional)
+path = os.path.join(G, f"{tag}train_launches.csv")
+if os.path.exists(path):
+    rows = [r for r in csv.reader(l for l in open(path) if not l.startswith("=="))]
+    hdr = rows[0]
+    ik, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        if len(r) <= iv:
+            continue
+        v = float(r[iv].replace(",", ""))
+        v = v / 1e3 if r[iu] in ("ns", "nsecond") else (v * 1e3 if r[iu] in ("ms", "msecond") else v)
+        name = r[ik].split("(")[0].replace("void ", "")[:90]
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    w(f"# {tag}: ncu launch list of the TRAIN STEP (bench.py --workload train_step --steps 2 --warmup 3 --no-e2e --cameras 1 --refine-every 3)")
+    w()
+    w("| kernel | launches | total us | share |")
+    w("|---|---:|---:|---:|")
+    for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
+        w(f"| `{n}` | {c} | {t:.1f} | {100 * t / tot:.1f}% |")
+    w()
+
 # ---- full captures
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -53,7 +78,8 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum",
         "l1tex__t_requests_pipe_lsu_mem_global_op_red.sum", "lts__t_sectors_op_red.sum",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__inst_executed_pipe_xu.sum"]
-for kern in ("render_bwd", "render_fwd", "preprocess_bwd", "pack", "duplicate", "preprocess", "sort"):
+for kern in ("render_bwd", "render_fwd", "preprocess_bwd", "pack", "duplicate", "preprocess", "sort", "adam", "ssim_fwd",
+             "ssim_bwd", "ref_render_bwd"):
     rep = os.path.join(G, f"{tag}_{kern}.ncu-rep")
     if not os.path.exists(rep):
         continue
