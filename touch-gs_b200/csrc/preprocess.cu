@@ -22,6 +22,38 @@ __device__ __forceinline__ void load_cam(const float* vm, const float* pm, const
     __syncthreads();
 }
 
+// ---- coalesced staging of the SH block (K = 16: 192 B per Gaussian, the bulk of this path's HBM traffic)
+// One thread per Gaussian reading its own 192 bytes makes every warp-wide 16-byte load touch 32 different lines.
+// Instead each WARP moves the 6 KB block of its 32 consecutive Gaussians between HBM and shared memory with fully
+// coalesced 16-byte accesses (12 independent loads in flight per lane), and the threads work on their own row in
+// shared memory.  Rows are padded from 12 to 13 float4 so that the per-thread float4 accesses of a quarter warp hit
+// 32 distinct banks.
+constexpr int kShRowF4 = 12;                 // float4 per Gaussian at K = 16
+constexpr int kShRowPad = kShRowF4 + 1;
+constexpr size_t kShStageBytes = (size_t)kBlock * kShRowPad * sizeof(float4);   // 53,248 B per CTA
+
+__device__ __forceinline__ void warp_stage_in(const float* __restrict__ g_base, int first, int N, float4* s_rows, int lane) {
+    const float4* src = reinterpret_cast<const float4*>(g_base) + (size_t)first * kShRowF4;
+    const int total = min(32, N - first) * kShRowF4;
+#pragma unroll
+    for (int it = 0; it < kShRowF4; ++it) {
+        const int e = it * 32 + lane;
+        if (e < total) s_rows[(e / kShRowF4) * kShRowPad + (e % kShRowF4)] = __ldg(src + e);
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void warp_stage_out(float* __restrict__ g_base, int first, int N, const float4* s_rows, int lane) {
+    __syncwarp();
+    float4* dst = reinterpret_cast<float4*>(g_base) + (size_t)first * kShRowF4;
+    const int total = min(32, N - first) * kShRowF4;
+#pragma unroll
+    for (int it = 0; it < kShRowF4; ++it) {
+        const int e = it * 32 + lane;
+        if (e < total) dst[e] = s_rows[(e / kShRowF4) * kShRowPad + (e % kShRowF4)];
+    }
+}
+
+template <bool STAGE>
 __global__ void __launch_bounds__(kBlock)
 k_preprocess(int N, const float* __restrict__ means, const float* __restrict__ scales,
              const float* __restrict__ rots, const float* __restrict__ opac,
@@ -33,8 +65,17 @@ k_preprocess(int N, const float* __restrict__ means, const float* __restrict__ s
              uint2* __restrict__ rect, uint32_t* __restrict__ depth_keys, uint32_t* __restrict__ ids,
              int32_t* __restrict__ radii) {
     __shared__ CamMats cm;
+    extern __shared__ __align__(16) float4 s_stage[];
     load_cam(vm, pm, campos, &cm);
     int i = blockIdx.x * kBlock + threadIdx.x;
+    float4* s_row = nullptr;
+    if (STAGE) {                                // every warp stages the SH block of its 32 Gaussians (K = 16)
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        float4* s_rows = s_stage + (size_t)warp * 32 * kShRowPad;
+        const int first = blockIdx.x * kBlock + warp * 32;
+        if (first < N) warp_stage_in(shs, first, N, s_rows, lane);
+        s_row = s_rows + lane * kShRowPad;
+    }
     if (i >= N) return;
     float x = means[3 * i], y = means[3 * i + 1], z = means[3 * i + 2];
     float cov[6];
@@ -51,8 +92,32 @@ k_preprocess(int N, const float* __restrict__ means, const float* __restrict__ s
     bool vis = tgs_project(cm.vm, cm.pm, cam, x, y, z, cov, p);
     float rgb[3] = {0.f, 0.f, 0.f};
     unsigned cl = 0;
-    if (vis) {
-        if (shs) {
+    if (vis && shs && STAGE) {
+        // colour straight from the staged row: four coefficients' worth of floats at a time, each channel accumulated
+        // in ascending-k order exactly like tgs_sh_forward (bit-identical), without a 48-register copy of the row
+        float b[16], acc[3] = {0.f, 0.f, 0.f};
+        tgs_sh_bases(cam.deg, x - cm.cp[0], y - cm.cp[1], z - cm.cp[2], b);
+        const int nf = 3 * (cam.deg + 1) * (cam.deg + 1);
+#pragma unroll
+        for (int k4 = 0; k4 < kShRowF4; ++k4) {
+            if (4 * k4 < nf) {
+                const float4 v = s_row[k4];
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int e = 4 * k4 + j;
+                    if (e < nf) acc[e % 3] += b[e / 3] * vv[j];
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float a = acc[c] + 0.5f;
+            if (a < 0.0f) { cl |= (1u << c); a = 0.0f; }
+            rgb[c] = a;
+        }
+    } else if (vis) {
+        if (shs && !STAGE) {
             // K*3 contiguous floats per Gaussian; 16-byte loads (K*12 B is a multiple of 16 for K in {1,4,9,16}
             // only when K*3 % 4 == 0, so fall back to scalar loads otherwise)
             float sh[48];
@@ -113,7 +178,8 @@ struct PeerGather {
     int row0[TGS_MAX_PEERS], row1[TGS_MAX_PEERS];  // tile-row band rendered by rank r
 };
 
-__global__ void __launch_bounds__(kBlock)
+template <bool STAGE>
+__global__ void __launch_bounds__(kBlock, 3)
 k_preprocess_bwd(int N, PeerGather pg, const TgsRecord* __restrict__ rec, const float* __restrict__ means, const float* __restrict__ scales,
                  const float* __restrict__ rots, const float* __restrict__ shs,
                  const float* __restrict__ covpre, const float* __restrict__ vm,
@@ -124,9 +190,16 @@ k_preprocess_bwd(int N, PeerGather pg, const TgsRecord* __restrict__ rec, const 
                  float* __restrict__ dopacity, float* __restrict__ dshs, float* __restrict__ dcolors,
                  float* __restrict__ dscales, float* __restrict__ drots, float* __restrict__ dcov3D) {
     __shared__ CamMats cm;
+    extern __shared__ __align__(16) float4 s_stage[];
     load_cam(vm, pm, campos, &cm);
     int i = blockIdx.x * kBlock + threadIdx.x;
-    if (i >= N) return;
+    // STAGE (K = 16): the warp's SH block comes in through shared memory, each thread turns its row into dL/dSH in
+    // place, and the block goes back out to `dshs` with coalesced stores
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4* s_rows = STAGE ? s_stage + (size_t)warp * 32 * kShRowPad : nullptr;
+    const int first = blockIdx.x * kBlock + warp * 32;
+    if (STAGE && first < N) warp_stage_in(shs, first, N, s_rows, lane);
+    if (i < N) {
     float dm[3] = {0.f, 0.f, 0.f}, dc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float ds[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
     float sg[TGS_NGRAD];
@@ -155,9 +228,15 @@ k_preprocess_bwd(int N, PeerGather pg, const TgsRecord* __restrict__ rec, const 
         for (int k = 0; k < 6; ++k) cov[k] = cov3D[6 * i + k];
         tgs_project_backward(cm.vm, cm.pm, cam, x, y, z, cov, sg, dm, dc);
         if (shs) {
-            // streams the K coefficients in groups of 4 straight from / to global memory
-            tgs_sh_backward(cam.deg, cam.K, shs + (size_t)3 * cam.K * i, x - cm.cp[0], y - cm.cp[1], z - cm.cp[2],
-                            sg + 6, clamped[i], dshs + (size_t)3 * cam.K * i, dm);
+            if (STAGE) {
+                float* row = reinterpret_cast<float*>(s_rows + lane * kShRowPad);
+                tgs_sh_backward(cam.deg, cam.K, row, x - cm.cp[0], y - cm.cp[1], z - cm.cp[2], sg + 6, clamped[i], row, dm,
+                                false);
+            } else {
+                // streams the K coefficients in groups of 4 straight from / to global memory
+                tgs_sh_backward(cam.deg, cam.K, shs + (size_t)3 * cam.K * i, x - cm.cp[0], y - cm.cp[1], z - cm.cp[2],
+                                sg + 6, clamped[i], dshs + (size_t)3 * cam.K * i, dm);
+            }
         }
         if (!covpre) {
             float4 q = reinterpret_cast<const float4*>(rots)[i];
@@ -166,8 +245,14 @@ k_preprocess_bwd(int N, PeerGather pg, const TgsRecord* __restrict__ rec, const 
             tgs_cov3d_backward(sc, cam.mod, qq, dc, ds, dq);
         }
     } else if (dshs) {
-        float* dst = dshs + (size_t)3 * cam.K * i;
-        for (int k = 0; k < 3 * cam.K; ++k) dst[k] = 0.0f;
+        if (STAGE) {
+            float4* row = s_rows + lane * kShRowPad;
+#pragma unroll
+            for (int k = 0; k < kShRowF4; ++k) row[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            float* dst = dshs + (size_t)3 * cam.K * i;
+            for (int k = 0; k < 3 * cam.K; ++k) dst[k] = 0.0f;
+        }
     }
     dmeans2D[3 * i] = sg[0] * 0.5f * (float)cam.W;
     dmeans2D[3 * i + 1] = sg[1] * 0.5f * (float)cam.H;
@@ -185,6 +270,8 @@ k_preprocess_bwd(int N, PeerGather pg, const TgsRecord* __restrict__ rec, const 
 #pragma unroll
         for (int k = 0; k < 6; ++k) dcov3D[6 * i + k] = dc[k];
     }
+    }   // i < N
+    if (STAGE && first < N) warp_stage_out(dshs, first, N, s_rows, lane);
 }
 
 __global__ void k_mark_visible(int N, const float* __restrict__ means, const float* __restrict__ vm,
@@ -197,12 +284,29 @@ __global__ void k_mark_visible(int N, const float* __restrict__ means, const flo
 
 }  // namespace
 
+// opt in to > 48 KB of dynamic shared memory for the staged kernels, once per device
+static cudaError_t enable_stage_smem() {
+    static bool done[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || done[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(k_preprocess<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShStageBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_preprocess_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShStageBytes);
+    if (e == cudaSuccess) done[dev] = true;
+    return e;
+}
+
 int tgs_launch_preprocess(const TgsCam& cam, const TgsSettings* s, const TgsGaussians* g,
                           GeomView gv, int32_t* radii, cudaStream_t st) {
     int N = g->N;
     if (N == 0) return 0;
     TgsProfScope prof(TGS_STAGE_PREPROCESS, st);
-    k_preprocess<<<(N + kBlock - 1) / kBlock, kBlock, 0, st>>>(
+    const bool stage = g->shs != nullptr && cam.K == 16;
+    TGS_CUDA(enable_stage_smem());
+    auto kern = stage ? k_preprocess<true> : k_preprocess<false>;
+    kern<<<(N + kBlock - 1) / kBlock, kBlock, stage ? kShStageBytes : 0, st>>>(
         N, g->means3D, g->scales, g->rotations, g->opacities, g->shs, g->colors_precomp,
         g->cov3D_precomp, s->viewmatrix, s->projmatrix, s->campos, cam, gv.records, gv.cov3D,
         gv.tiles_touched, gv.clamped, gv.rect, gv.depth_keys, gv.ids, radii);
@@ -225,7 +329,10 @@ int tgs_launch_preprocess_bwd(const TgsCam& cam, const TgsSettings* s, const Tgs
         for (int r = 0; r < world; ++r) { pg.ptr[r] = peer_grads[r]; pg.row0[r] = peer_rows[2 * r]; pg.row1[r] = peer_rows[2 * r + 1]; }
     }
     TgsProfScope prof(TGS_STAGE_PREPROCESS_BWD, st);
-    k_preprocess_bwd<<<(N + kBlock - 1) / kBlock, kBlock, 0, st>>>(
+    const bool stage = g->shs != nullptr && cam.K == 16;
+    TGS_CUDA(enable_stage_smem());
+    auto kern = stage ? k_preprocess_bwd<true> : k_preprocess_bwd<false>;
+    kern<<<(N + kBlock - 1) / kBlock, kBlock, stage ? kShStageBytes : 0, st>>>(
         N, pg, gv.records, g->means3D, g->scales, g->rotations, g->shs, g->cov3D_precomp, s->viewmatrix,
         s->projmatrix, s->campos, cam, gv.cov3D, gv.clamped, radii, screen_grads, gr->dmeans2D,
         gr->dmeans3D, gr->dopacity, g->shs ? gr->dshs : nullptr, gr->dcolors, gr->dscales,

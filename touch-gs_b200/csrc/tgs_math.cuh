@@ -167,13 +167,10 @@ TGS_HD bool tgs_project(const float* vm, const float* pm, const TgsCam& cam,
 
 // --------------------------------------------------------------------------------- SH colour
 // sh: [K][3] for this Gaussian.  Returns rgb (+0.5, clamped >= 0) and the clamp mask (bit c).
-TGS_HD void tgs_sh_forward(int deg, const float* sh, float dx, float dy, float dz,
-                           float* rgb, unsigned& clamped) {
-    // NOTE: `sh` must hold 48 floats with zeros above the active degree: all loops below run over
-    // the full 16 bases with compile-time indices so that device code keeps everything in registers.
+// the 16 real-SH basis values at direction (dx,dy,dz)/|.| (zero above the active degree)
+TGS_HD void tgs_sh_bases(int deg, float dx, float dy, float dz, float* b) {
     float ln = sqrtf((dx * dx + dy * dy) + dz * dz);
     float x = dx / ln, y = dy / ln, z = dz / ln;
-    float b[16];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -196,6 +193,14 @@ TGS_HD void tgs_sh_forward(int deg, const float* sh, float dx, float dy, float d
             }
         }
     }
+}
+
+TGS_HD void tgs_sh_forward(int deg, const float* sh, float dx, float dy, float dz,
+                           float* rgb, unsigned& clamped) {
+    // NOTE: `sh` must hold 48 floats with zeros above the active degree: all loops below run over
+    // the full 16 bases with compile-time indices so that device code keeps everything in registers.
+    float b[16];
+    tgs_sh_bases(deg, dx, dy, dz, b);
     clamped = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -273,7 +278,8 @@ TGS_HD void tgs_sh_backward_group(int grp, int nb, float x, float y, float z, co
 // direction.  drgb is zeroed where the forward clamped.  `sh` / `dsh` may be global pointers: they are
 // read / written in groups of 4 coefficients.
 TGS_HD void tgs_sh_backward(int deg, int K, const float* sh, float dx, float dy, float dz,
-                            const float* drgb_in, unsigned clamped, float* dsh, float* dmean) {
+                            const float* drgb_in, unsigned clamped, float* dsh, float* dmean,
+                            bool sh_in_global = true) {   // false: `sh` points into shared memory (no ld.global.nc)
     float g[3];
     for (int c = 0; c < 3; ++c) g[c] = ((clamped >> c) & 1u) ? 0.0f : drgb_in[c];
     const float ln = sqrtf((dx * dx + dy * dy) + dz * dz);
@@ -292,7 +298,9 @@ TGS_HD void tgs_sh_backward(int deg, int K, const float* sh, float dx, float dy,
 #if defined(__CUDA_ARCH__)
             if (4 * grp < nb) {
                 const float4* p = reinterpret_cast<const float4*>(sh + 12 * grp);
-                const float4 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2);
+                float4 v0, v1, v2;
+                if (sh_in_global) { v0 = __ldg(p); v1 = __ldg(p + 1); v2 = __ldg(p + 2); }
+                else { v0 = p[0]; v1 = p[1]; v2 = p[2]; }
                 s12[0] = v0.x; s12[1] = v0.y; s12[2] = v0.z; s12[3] = v0.w; s12[4] = v1.x; s12[5] = v1.y;
                 s12[6] = v1.z; s12[7] = v1.w; s12[8] = v2.x; s12[9] = v2.y; s12[10] = v2.z; s12[11] = v2.w;
             } else {
