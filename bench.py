@@ -329,7 +329,7 @@ class TrainStepper(Stepper):
                torch.log(params["scales"].detach()), params["rotations"].detach()]
         tc = T.TrainConfig(sh_degree=cfg["sh_degree"], depth_loss_mult=DEPTH_LOSS_MULT,
                            depth_loss_type="DEPTH_UNCERTAINTY_WEIGHTED_LOSS", uncertainty_weight=1.0,
-                           refine_every=refine_every, warmup_length=0)
+                           refine_every=refine_every, warmup_length=0, sh_degree_interval=0)
         self.trainer = T.TouchGSTrainer(*raw, tc, process_group=group)
         self.raw_n = int(raw[0].shape[0])
         self.n_history = [self.trainer.num_points]

@@ -75,7 +75,7 @@ def main():
     # ---- trainer: sharded (band + halo) vs single GPU
     raw = [sc.means3D, sc.shs, torch.logit(sc.opacities.reshape(-1).clamp(1e-4, 1 - 1e-4)), torch.log(sc.scales), sc.rotations]
     raw = [t.to(dev) for t in raw]
-    cfg = T.TrainConfig(sh_degree=deg, depth_loss_type="DEPTH_UNCERTAINTY_WEIGHTED_LOSS", refine_every=0)
+    cfg = T.TrainConfig(sh_degree=deg, depth_loss_type="DEPTH_UNCERTAINTY_WEIGHTED_LOSS", refine_every=0, sh_degree_interval=0)
     single = T.TouchGSTrainer(*raw, cfg)
     l_full = single.train_step(rs, gt, tgt, wgt)
     for name, px in (("nccl", None), ("p2p", peer)):

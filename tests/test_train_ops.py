@@ -183,7 +183,7 @@ def test_train_step_matches_oracle_and_adam_moves_parameters():
     base = O.rasterize(sc.means3D, sc.opacities, oracle_settings(cam, c["deg"]), shs=sc.shs, scales=sc.scales, rotations=sc.rotations)
     tgt, wgt = synth.make_touch_maps(base.depth[0] + 0.02, seed=1, n_patches=3, patch_radius=12)
     cfg = T.TrainConfig(sh_degree=c["deg"], depth_loss_type="DEPTH_UNCERTAINTY_WEIGHTED_LOSS", uncertainty_weight=2.0,
-                        refine_every=0)
+                        refine_every=0, sh_degree_interval=0)
     raw, ref_g, ref_out = _oracle_train_grads(sc, cam, c["deg"], gt, tgt, wgt / 2.0, cfg)
     tr = T.TouchGSTrainer(*[raw[k].to(DEV) for k in ("means", "shs", "opacity_logit", "scales_log", "quats")], cfg)
     before = {k: v.clone() for k, v in tr.p.items()}
@@ -209,7 +209,8 @@ def test_trainer_refine_changes_population_consistently():
     sc = synth.make_scene(4000, 1, 0.004, 0.06, seed=12)
     cam = synth.look_at_camera(160, 128, (0.3, 0.2, -3.0))
     raw = [sc.means3D, sc.shs, torch.logit(sc.opacities.reshape(-1).clamp(1e-4, 1 - 1e-4)), torch.log(sc.scales), sc.rotations]
-    cfg = T.TrainConfig(sh_degree=1, refine_every=2, warmup_length=0, densify_grad_thresh=1e-7, reset_alpha_every=1)
+    cfg = T.TrainConfig(sh_degree=1, refine_every=2, warmup_length=0, densify_grad_thresh=1e-7, reset_alpha_every=1,
+                        sh_degree_interval=2)
     tr = T.TouchGSTrainer(*[t.to(DEV) for t in raw], cfg)
     rs = cuda_settings(cam, 1, DEV)
     gt = torch.rand(3, 128, 160, device=DEV)
@@ -223,5 +224,10 @@ def test_trainer_refine_changes_population_consistently():
         assert all(t.shape[0] == n1 for t in d.values())
     assert tr.grad_accum.shape[0] == n1 and int(tr.vis_count.sum()) == 0
     assert float(torch.sigmoid(tr.p["opacity_logit"]).max()) <= 2 * cfg.cull_alpha_thresh + 1e-6
+    # SH degree schedule (interval 2): steps 1 were degree 0 -> the higher bands got no gradient there; step 3 is degree 1
     l = tr.train_step(rs, gt)                              # the resized state keeps training
     assert math.isfinite(float(l))
+    assert float(tr.last["grads"]["shs"][:, 1:].abs().sum()) > 0.0
+    fresh = T.TouchGSTrainer(*[t.to(DEV) for t in raw], cfg)
+    fresh.train_step(rs, gt)
+    assert float(fresh.last["grads"]["shs"][:, 1:].abs().sum()) == 0.0 and float(fresh.last["grads"]["shs"][:, 0].abs().sum()) > 0.0

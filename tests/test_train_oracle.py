@@ -82,4 +82,9 @@ def test_trainer_rejects_cpu_tensors_and_bad_loss_type(tgs_lib):
         T.TouchGSTrainer(z(4, 3), z(4, 16, 3), z(4), z(4, 3), z(4, 4), T.TrainConfig(depth_loss_type="NOPE"))
     with pytest.raises(RuntimeError, match="CUDA-only"):
         T.photometric_loss(z(3, 8, 8), z(3, 8, 8))
-    assert T.TrainConfig().adam_eps == 1e-15 and T.TrainConfig().depth_loss_mult == 0.2
+    c = T.TrainConfig()
+    assert c.adam_eps == 1e-15 and c.depth_loss_mult == 0.2 and c.max_steps == 30000
+    # position learning rate: log-linear decay 1.6e-4 -> 1.6e-6; SH degree: +1 every 1000 steps up to sh_degree
+    assert c.lr_means_at(0) == 1.6e-4 and abs(c.lr_means_at(15000) - 1.6e-5) < 1e-9 and abs(c.lr_means_at(10**6) - 1.6e-6) < 1e-12
+    assert [c.active_sh_degree(s) for s in (1, 999, 1000, 2500, 99999)] == [0, 0, 1, 2, 3]
+    assert T.TrainConfig(sh_degree_interval=0).active_sh_degree(1) == 3

@@ -150,7 +150,10 @@ class TrainConfig:
     depth_loss_type: str = "SIMPLE_LOSS"         # reference scripts/train_bunny_blender.sh:50 / train_bunny_real.sh:52
     uncertainty_weight: float = 1.0              # reference scripts/train_bunny_real.sh:52
     depth_loss: str = "l1"
-    lr_means: float = 1.6e-4
+    lr_means: float = 1.6e-4                     # initial; decays exponentially to lr_means_final over max_steps
+    lr_means_final: float = 1.6e-6
+    max_steps: int = 30000                       # reference legacy/config_tactile.py:28 (max_num_iterations)
+    sh_degree_interval: int = 1000               # active SH degree = min(step // interval, sh_degree); 0 = always full
     lr_features_dc: float = 2.5e-3
     lr_features_rest: float = 2.5e-3 / 20.0
     lr_opacity: float = 5e-2
@@ -169,6 +172,19 @@ class TrainConfig:
     n_split_samples: int = 2
     split_shrink: float = 1.6
     seed: int = 0
+
+    def lr_means_at(self, step: int) -> float:
+        """Exponential decay of the position learning rate (log-linear interpolation, the scheduler of the splat
+        trainers of that era)."""
+        if self.max_steps <= 0 or self.lr_means_final <= 0 or self.lr_means_final == self.lr_means:
+            return self.lr_means
+        t = min(max(step / float(self.max_steps), 0.0), 1.0)
+        return math.exp(math.log(self.lr_means) * (1.0 - t) + math.log(self.lr_means_final) * t)
+
+    def active_sh_degree(self, step: int) -> int:
+        if self.sh_degree_interval <= 0:
+            return self.sh_degree
+        return min(step // self.sh_degree_interval, self.sh_degree)
 
     def densify_struct(self) -> "L.TgsDensifyConfig":
         return L.TgsDensifyConfig(grad_thresh=self.densify_grad_thresh, size_thresh=self.densify_size_thresh,
@@ -278,6 +294,10 @@ class TouchGSTrainer:
         cfg, p = self.cfg, self.p
         lib = L.load()
         self.step += 1
+        # SH degree schedule: the settings' sh_degree is an upper bound; the active degree grows with the step
+        deg = min(int(rs.sh_degree), cfg.active_sh_degree(self.step))
+        if deg != int(rs.sh_degree):
+            rs = rs._replace(sh_degree=deg)
         H, W = int(rs.image_height), int(rs.image_width)
         N = self.num_points
         tile_rows, loss_rows, grad_rows = self._bands(H)
@@ -310,7 +330,8 @@ class TouchGSTrainer:
                                           _ptr(self.max_radii), _stream_ptr(self.dev)), "tgs_densify_stats")
             K = int(p["shs"].shape[1])
             adam_step([
-                dict(param=p["means"], grad=g["means"], exp_avg=self.m["means"], exp_avg_sq=self.v["means"], lr=cfg.lr_means),
+                dict(param=p["means"], grad=g["means"], exp_avg=self.m["means"], exp_avg_sq=self.v["means"],
+                     lr=cfg.lr_means_at(self.step)),
                 dict(param=p["shs"], grad=g["shs"], exp_avg=self.m["shs"], exp_avg_sq=self.v["shs"], lr=cfg.lr_features_dc,
                      lr_tail=cfg.lr_features_rest, period=3 * K, head=3),
                 dict(param=p["opacity_logit"], grad=g["opacity_logit"], exp_avg=self.m["opacity_logit"],
