@@ -110,3 +110,28 @@ def test_two_rank_gloo_matches_single_rank():
         assert float((sg_r - sg).abs().max()) <= 1e-4 * float(sg.abs().max())
         assert float((gm - m.grad).abs().max()) <= 1e-4 * float(m.grad.abs().max())
     assert torch.equal(res[0][1], res[1][1])                       # replicas stay in sync
+
+
+def test_halo_bands_cover_the_image_and_the_ssim_window():
+    """Sharded train step: loss rows partition the image, rendered rows add >= 5 rows (the SSIM window
+    radius) on every interior border, gradient rows == rendered rows."""
+    from helpers import T
+    S = T.sharding
+    for H in (1080, 2160, 272, 117, 16):
+        for world in (1, 2, 4, 8):
+            if world > S.tile_rows(H):
+                continue
+            hb = S.halo_bands(H, world)
+            assert len(hb) == world
+            rows = []
+            for r, (ext, loss, grad) in enumerate(hb):
+                assert grad == S.band_pixel_rows(ext, H)
+                assert grad[0] <= loss[0] <= loss[1] <= grad[1]
+                if loss[1] > loss[0]:
+                    if loss[0] > 0:
+                        assert loss[0] - grad[0] >= 5
+                    if loss[1] < H:
+                        assert grad[1] - loss[1] >= 5
+                rows.append(loss)
+            assert rows[0][0] == 0 and rows[-1][1] == H
+            assert all(rows[i][1] == rows[i + 1][0] for i in range(world - 1)), "loss rows must partition the image"

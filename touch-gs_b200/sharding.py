@@ -50,6 +50,19 @@ def band_pixel_rows(band: Tuple[int, int], image_height: int) -> Tuple[int, int]
     return min(band[0] * TILE, image_height), min(band[1] * TILE, image_height)
 
 
+def halo_bands(image_height: int, world_size: int, halo_tiles: int = 1):
+    """Bands of the sharded TRAIN STEP: per rank (tile rows to render incl. halo, loss pixel rows, gradient pixel
+    rows).  The 11x11 SSIM window reaches 5 rows across a band border, so every rank renders `halo_tiles` extra tile
+    rows on each side; its loss (and touch loss) pixels stay its own band; its image gradient covers band + halo."""
+    Ty = tile_rows(image_height)
+    own = even_bands(image_height, world_size)
+    out = []
+    for b0, b1 in own:
+        ext = (max(0, b0 - halo_tiles), min(Ty, b1 + halo_tiles))
+        out.append((ext, band_pixel_rows((b0, b1), image_height), band_pixel_rows(ext, image_height)))
+    return out
+
+
 def all_reduce_screen_grads(sgrad, group=None):
     """The single exchange step: sum the [N,10] partial screen-space gradients over ranks."""
     import torch.distributed as dist

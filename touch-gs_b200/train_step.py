@@ -275,12 +275,10 @@ class TouchGSTrainer:
             return None, None, None
         import torch.distributed as dist
         world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-        Ty = (H + TILE - 1) // TILE
-        own = sharding.even_bands(H, world)
-        ext = [(max(0, b0 - 1), min(Ty, b1 + 1)) for b0, b1 in own]    # + one tile row of halo on each side
+        hb = sharding.halo_bands(H, world)                              # + one tile row of halo on each side
         if self.peer is not None:
-            self.peer.bands = ext
-        return ext[rank], sharding.band_pixel_rows(own[rank], H), sharding.band_pixel_rows(ext[rank], H)
+            self.peer.bands = [b[0] for b in hb]
+        return hb[rank]
 
     def touch_weight(self, touch_weight):
         """SIMPLE_LOSS: unweighted.  DEPTH_UNCERTAINTY_WEIGHTED_LOSS: w = (1/sigma) / uncertainty_weight, the
