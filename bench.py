@@ -259,7 +259,14 @@ class Stepper:
         with torch.cuda.stream(self.copy_stream):
             for k, v in b["host"].items():
                 if k in ("gt", "target", "weight") and (r0, r1) != (0, self.cfg["H"]):
-                    self.stage[slot][k][..., r0:r1, :].copy_(v[..., r0:r1, :], non_blocking=True)
+                    # one CONTIGUOUS row range per channel: a strided [3, rows, W] slice would make torch stage the
+                    # copy through a pageable temporary (synchronous, and a host memcpy on top)
+                    dst = self.stage[slot][k]
+                    if v.dim() == 3:
+                        for c in range(v.shape[0]):
+                            dst[c, r0:r1].copy_(v[c, r0:r1], non_blocking=True)
+                    else:
+                        dst[r0:r1].copy_(v[r0:r1], non_blocking=True)
                 else:
                     self.stage[slot][k].copy_(v, non_blocking=True)
             self.ready[slot].record(self.copy_stream)
