@@ -300,6 +300,12 @@ class _RasterizeGaussians(torch.autograd.Function):
                                    row_begin=0 if opt.touch_rows is None else int(opt.touch_rows[0]),
                                    row_end=0 if opt.touch_rows is None else int(opt.touch_rows[1]))
             peer = opt.peer_exchange if N > 0 else None
+            if peer is not None and N > peer.capacity:
+                # more Gaussians than the peer-mapped buffers were sized for (the population grew at a refine step):
+                # every rank sees the same N, so all of them take the all-reduce path for this call
+                if opt.process_group is None:
+                    raise ValueError(f"PeerScreenGrads capacity {peer.capacity} < {N} Gaussians and no process_group to fall back to")
+                peer = None
             if peer is not None:
                 sgrad, peer_ptrs, peer_handle = peer.acquire(N)     # this rank's peer-mapped buffer of the step
             else:
