@@ -240,6 +240,15 @@ class _RasterizeGaussians(torch.autograd.Function):
             scratch.disarm()
             if scratch.error is not None:
                 raise scratch.error
+            if rc != 0 and rs.debug:
+                # reference-era operator habit (SURVEY §8b "Errors"): with debug=True a failing forward leaves its
+                # arguments behind for post-mortem inspection
+                try:
+                    torch.save(dict(means3D=means3D, opacities=opacities, shs=sh, colors_precomp=colors_precomp, scales=scales,
+                                    rotations=rotations, cov3D_precomp=cov3Ds_precomp, settings=tuple(rs)), "snapshot_fw.dump")
+                    print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                except Exception:  # noqa: BLE001 - the dump is best effort; the real error is raised below
+                    pass
             L.check(rc, "tgs_forward")
 
         ctx.rs, ctx.opt, ctx.K = rs, opt, K
