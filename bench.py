@@ -567,10 +567,12 @@ def main():
             T._lib.profile_read()
         own0, cub0 = T._lib.launch_counts()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]     # per-step spread (p10/p50/p90)
         t_begin = time.time()
         e0.record()
         for i in range(steps):
             fn(warmup + i)
+            marks[i].record()
         if finalize is not None:
             finalize()
         e1.record()
@@ -579,6 +581,8 @@ def main():
         sampler.stop()
         clocks = sampler.summary(t_begin, t_end, t_warm)
         ms = e0.elapsed_time(e1)
+        per = sorted(a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks))
+        timed.spread = {"p10": per[len(per) // 10], "p50": per[len(per) // 2], "p90": per[(9 * len(per)) // 10]} if per else None
         prof = None
         if profile:
             prof = T._lib.profile_read()
@@ -594,6 +598,7 @@ def main():
     ms, clocks, prof, (own, cub) = timed(lambda i: stepper.device_step(batches[i % len(batches)]), steps, warmup,
                                          profile=True)
     value = N * steps / (ms * 1e-3)
+    spread = getattr(timed, "spread", None)
 
     # measured I (num_rendered) of the cameras used: read from a state-inspecting forward (untimed)
     with torch.no_grad():
@@ -692,7 +697,7 @@ def main():
     out = {
         "metric": METRIC if not train_mode else "full train step Gaussians/sec (BASELINE config c5 pipeline: rasterizer fwd+bwd + L1/SSIM + fused touch depth-L1 + Adam + refine)",
         "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms / steps, "ms_per_step_spread": spread, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.config}: {N} Gaussians, {W}x{H}, SH deg {cfg['sh_degree']}, fused touch depth-L1 "
                                f"(mult {DEPTH_LOSS_MULT}), {len(batches)} orbit cameras cycled",
