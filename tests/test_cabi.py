@@ -100,3 +100,86 @@ def test_scratch_allocator_has_no_reference_cycle(tgs_lib):
         assert w() is None, "scratch buffer survived refcount release: reference cycle"
     finally:
         gc.enable()
+
+
+def test_new_entry_points_validate_arguments_without_gpu(tgs_lib):
+    """Train-step, screen-space and multi-GPU entry points reject bad arguments before touching a device."""
+    L = T._lib
+    lib = tgs_lib
+    assert lib.tgs_photometric_loss_forward(None, None, 8, 8, 0, 0, 0.2, None, None, None, None) == -1
+    assert b"tgs_photometric_loss_forward" in lib.tgs_last_error()
+    assert lib.tgs_photometric_loss_backward(None, None, None, 8, 8, 0, 0, 0, 0, 0.2, None, None, None) == -1
+    assert lib.tgs_photometric_scratch_floats(10, 7) == 9 * 70
+    assert lib.tgs_activate_forward(4, None, None, None, None, None, None, None) == -1
+    assert lib.tgs_activate_forward(0, None, None, None, None, None, None, None) == 0            # empty input is fine
+    g = (L.TgsAdamGroup * 1)(L.TgsAdamGroup(param=0x1000, grad=0x1000, exp_avg=0x1000, exp_avg_sq=0x1004, numel=16, lr=1e-3,
+                                            lr_tail=1e-3, period=0, head=0))
+    assert lib.tgs_adam_step(g, 1, 1, 0.9, 0.999, 1e-15, None) == -1 and b"16-byte aligned" in lib.tgs_last_error()
+    assert lib.tgs_adam_step(g, 0, 1, 0.9, 0.999, 1e-15, None) == -1
+    assert lib.tgs_adam_step(g, 1, 0, 0.9, 0.999, 1e-15, None) == -1                            # step counts from 1
+    g[0].exp_avg_sq = 0x1000
+    g[0].period, g[0].head = 48, 49
+    assert lib.tgs_adam_step(g, 1, 1, 0.9, 0.999, 1e-15, None) == -1 and b"period/head" in lib.tgs_last_error()
+    assert lib.tgs_densify_stats(5, None, None, None, None, None, None) == -1
+    cfg = L.TgsDensifyConfig(grad_thresh=2e-4, size_thresh=0.01, cull_alpha_thresh=0.1, cull_scale_thresh=0.5,
+                             split_shrink=1.6, n_split_samples=99)
+    tot = C.c_int64(0)
+    assert lib.tgs_densify_plan(0, None, None, None, None, C.byref(cfg), 1, None, None, None, 0, C.byref(tot), None) == -1
+    assert lib.tgs_densify_plan(8, 0x1000, 0x1000, 0x1000, 0x1000, C.byref(cfg), 1, 0x1000, 0x1000, 0x1000, 1024,
+                                C.byref(tot), None) == -1 and b"n_split_samples" in lib.tgs_last_error()
+    assert lib.tgs_densify_temp_bytes(1000) >= 256
+    s = L.TgsSettings(image_width=64, image_height=64, tanfovx=0.5, tanfovy=0.5, scale_modifier=1.0)
+    gg = L.TgsGaussians(N=4)
+    saved = L.TgsSaved()
+    cb = L.ALLOC_FN(lambda u, w, n: None)
+    assert lib.tgs_project_gaussians(C.byref(s), C.byref(gg), cb, None, None, C.byref(saved), None) == -1
+    assert b"viewmatrix" in lib.tgs_last_error()
+    assert lib.tgs_rasterize_screen_forward(C.byref(s), 4, None, None, None, None, None, None, 0.5, cb, None, None, None, None,
+                                            C.byref(saved), None) == -1
+    assert lib.tgs_spherical_harmonics(4, 5, 16, None, None, None, None) == -1                  # degree > 3
+    assert lib.tgs_spherical_harmonics(4, 3, 9, 0x1000, 0x1000, 0x1000, None) == -1             # K < (deg+1)^2
+    s.viewmatrix = s.projmatrix = s.bg = s.campos = 0x1000
+    gg.means3D = gg.opacities = gg.colors_precomp = gg.scales = gg.rotations = 0x1000
+    saved.geom = 0x1000
+    ptrs = (C.c_void_p * 2)(0x1000, 0)
+    rows = (C.c_int32 * 4)(0, 2, 2, 4)
+    gr = L.TgsGrads()
+    assert lib.tgs_backward_preprocess_gather(C.byref(s), C.byref(gg), C.byref(saved), 0x1000, ptrs, rows, 0, C.byref(gr), None) == -1
+    assert lib.tgs_backward_preprocess_gather(C.byref(s), C.byref(gg), C.byref(saved), 0x1000, ptrs, rows, 9, C.byref(gr), None) == -1
+    assert lib.tgs_backward_preprocess_gather(C.byref(s), C.byref(gg), C.byref(saved), 0x1000, ptrs, rows, 2, C.byref(gr), None) == -1
+    assert b"peer 1 pointer is NULL" in lib.tgs_last_error()
+    lay = L.TgsRefBinningLayout()
+    assert lib.tgs_refstructure_binning_layout(100, 1000, 64, C.byref(lay)) == 0
+    assert lay.keys_sorted >= lay.keys_unsorted + 8000 and lay.total % 256 == 0
+
+
+def test_struct_sizes_match_header(tgs_lib):
+    """ctypes mirrors vs the C structs: compile a tiny C program against include/tgs.h and compare sizeof()."""
+    import subprocess
+    import tempfile
+    L = T._lib
+    names = ["TgsSettings", "TgsGaussians", "TgsTouch", "TgsSaved", "TgsGrads", "TgsGeomLayout", "TgsBinningLayout",
+             "TgsImageLayout", "TgsRefBinningLayout", "TgsAdamGroup", "TgsDensifyConfig", "TgsParamSet"]
+    src = '#include <stdio.h>\n#include "tgs.h"\nint main(void){' + "".join(
+        f'printf("{n} %zu\\n", sizeof({n}));' for n in names) + "return 0;}\n"
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "s"), os.path.join(d, "s.c")], check=True)
+        out = subprocess.run([os.path.join(d, "s")], capture_output=True, text=True, check=True).stdout
+    sizes = dict(line.split() for line in out.strip().splitlines())
+    for n in names:
+        assert int(sizes[n]) == C.sizeof(getattr(L, n)), f"{n}: C {sizes[n]} != ctypes {C.sizeof(getattr(L, n))}"
+
+
+def test_gsplat_style_surface_rejects_cpu_tensors(tgs_lib):
+    import torch
+    from importlib import import_module
+    G = import_module("touch-gs_b200.gsplat_compat")
+    z = torch.zeros
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        G.project_gaussians(z(4, 3), z(4, 3), 1.0, torch.ones(4, 4), torch.eye(4), torch.eye(4), 100.0, 100.0, 32.0, 32.0, 64, 64)
+    with pytest.raises(ValueError, match="C <= 3"):
+        G.rasterize_gaussians(z(4, 2), z(4), z(4, dtype=torch.int32), z(4, 3), z(4, dtype=torch.int32), z(4, 5), z(4, 1), 64, 64)
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        G.spherical_harmonics(3, z(4, 3), z(4, 16, 3))
+    assert G.PIXEL_CENTER_OFFSET == 0.5 and G.ALPHA_MAX == 0.999
