@@ -22,7 +22,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib as L
-from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, _ptr, _stream_ptr, TILE
+from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, _ptr, _stream_ptr
 from . import sharding
 
 DEPTH_LOSS_TYPES = ("SIMPLE_LOSS", "DEPTH_UNCERTAINTY_WEIGHTED_LOSS")
