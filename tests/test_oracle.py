@@ -170,3 +170,42 @@ def test_fixture_scene_and_zbuffer_match_reference_function():
         f = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "fixture_scene.npz"))["focus"])
         v = cam.viewmatrix.t() @ torch.cat([f, torch.ones(1)])
         assert abs(float(v[0])) < 1e-4 and abs(float(v[1])) < 1e-4 and 0.3 < float(v[2]) < 0.8
+
+
+def test_oracle_convention_switches_are_self_consistent():
+    """SURVEY A.3 switches of the oracle (used by the gsplat-style surface tests): sampling at (x+0.5, y+0.5) equals
+    integer sampling of splats moved by -0.5; the principal point shifts the pixel means by exactly that many pixels;
+    near_z moves the cull plane; alpha_max only matters where o*G exceeds the smaller clamp."""
+    from helpers import O, synth
+    sc = synth.make_scene(400, 0, 0.03, 0.3, seed=21)
+    cam = synth.look_at_camera(96, 80, (0.2, 0.1, -2.4))
+    g = torch.Generator().manual_seed(0)
+    colors = torch.rand(400, 3, generator=g)
+    base = dict(image_height=80, image_width=96, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=torch.zeros(3), scale_modifier=1.0,
+                viewmatrix=cam.viewmatrix, projmatrix=cam.projmatrix, sh_degree=0, campos=cam.campos)
+    S0 = O.OracleSettings(**base)
+    S1 = O.OracleSettings(**base, pixel_offset=0.5)
+    pre = O.preprocess(sc.means3D, sc.scales, sc.rotations, sc.opacities, None, colors, None, S0)
+    bins = O.bin_and_sort(pre, S0)
+    a = O.render_tiles(pre, bins, S1)
+    b = O.render_tiles(pre._replace(xy=pre.xy - 0.5), bins, S0)
+    assert torch.allclose(a.color, b.color, atol=1e-6) and torch.equal(a.n_contrib, b.n_contrib)
+    Sp = O.OracleSettings(**base, principal=(3.25, -2.5))
+    prep = O.preprocess(sc.means3D, sc.scales, sc.rotations, sc.opacities, None, colors, None, Sp)
+    vis = (pre.radii > 0) & (prep.radii > 0)
+    assert torch.allclose(prep.xy[vis] - pre.xy[vis], torch.tensor([3.25, -2.5]).expand(int(vis.sum()), 2), atol=1e-4)
+    assert torch.equal(prep.radii[vis], pre.radii[vis]) and torch.allclose(prep.conic[vis], pre.conic[vis])
+    # near plane: a Gaussian at view depth 0.1 is culled at 0.2 and kept at 0.01
+    fwd = cam.viewmatrix[:3, 2]                     # world-space direction of +z in view space (transposed matrix: column 2)
+    near = (cam.campos + 0.1 * fwd)[None]
+    kw = dict(scales=torch.full((1, 3), 0.01), rotations=torch.tensor([[1.0, 0, 0, 0]]), opacities=torch.tensor([[0.5]]))
+    p_far = O.preprocess(near, kw["scales"], kw["rotations"], kw["opacities"], None, torch.ones(1, 3), None, S0)
+    p_near = O.preprocess(near, kw["scales"], kw["rotations"], kw["opacities"], None, torch.ones(1, 3), None,
+                          O.OracleSettings(**base, near_z=0.01))
+    assert int(p_far.radii[0]) == 0 and int(p_near.radii[0]) > 0 and abs(float(p_near.depth[0]) - 0.1) < 1e-5
+    # alpha clamp: an opaque splat's peak alpha is the clamp itself
+    one = O.preprocess(torch.zeros(1, 3), torch.full((1, 3), 0.3), kw["rotations"], torch.tensor([[1.0]]), None, torch.ones(1, 3), None, S0)
+    b1 = O.bin_and_sort(one, S0)
+    lo = O.render_tiles(one, b1, S0).alpha.max()
+    hi = O.render_tiles(one, b1, O.OracleSettings(**base, alpha_max=0.999)).alpha.max()
+    assert abs(float(lo) - 0.99) < 1e-3 and float(hi) > 0.995
