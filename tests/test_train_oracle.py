@@ -88,3 +88,21 @@ def test_trainer_rejects_cpu_tensors_and_bad_loss_type(tgs_lib):
     assert c.lr_means_at(0) == 1.6e-4 and abs(c.lr_means_at(15000) - 1.6e-5) < 1e-9 and abs(c.lr_means_at(10**6) - 1.6e-6) < 1e-12
     assert [c.active_sh_degree(s) for s in (1, 999, 1000, 2500, 99999)] == [0, 0, 1, 2, 3]
     assert T.TrainConfig(sh_degree_interval=0).active_sh_degree(1) == 3
+
+
+def test_train_oracle_regression_fixture():
+    """tests/golden/train_oracle_small.npz pins the train-step oracle against accidental change (a regression
+    fixture generated by the oracle itself, not a reference-side vector)."""
+    import os
+    import numpy as np
+    from importlib import import_module
+    from helpers import ROOT
+    mk = import_module("golden.make_train_golden")
+    got = mk.compute()
+    z = np.load(os.path.join(ROOT, "tests", "golden", "train_oracle_small.npz"))
+    assert set(z.files) == set(got)
+    for k in z.files:
+        if z[k].dtype.kind in "iub":
+            assert np.array_equal(z[k], got[k]), k
+        else:
+            assert np.allclose(z[k], got[k], rtol=1e-5, atol=1e-7), k
