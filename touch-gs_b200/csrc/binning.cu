@@ -28,8 +28,11 @@ struct TilesInOrder {
 };
 using TilesIt = cub::TransformInputIterator<uint32_t, TilesInOrder, cub::CountingInputIterator<uint32_t>>;
 
-// Emission in depth order.  One warp per 32 consecutive depth ranks; for each rank with tiles > 0 the
-// whole warp writes that Gaussian's tile list cooperatively (coalesced 2/4-byte stores).
+// Emission in depth order.  One warp per 32 consecutive depth ranks.  The scan makes the instances of those 32
+// Gaussians ONE contiguous output range [B, E), so the warp walks that range 32 slots at a time -- every store is a
+// full coalesced line -- and each lane finds the Gaussian that owns its slot by a 5-step binary search over the 32
+// inclusive offsets held one per lane (shuffles), instead of the warp serialising over its Gaussians with a third of
+// the lanes busy.
 template <typename KeyT>
 __global__ void __launch_bounds__(256)
 k_emit(int N, const uint32_t* __restrict__ order, const uint32_t* __restrict__ tiles,
@@ -37,29 +40,40 @@ k_emit(int N, const uint32_t* __restrict__ order, const uint32_t* __restrict__ t
        KeyT* __restrict__ keys, uint32_t* __restrict__ vals) {
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * blockDim.x + threadIdx.x;          // depth rank
-    uint32_t id = 0, cnt = 0, end = 0;
+    const int r_first = r - lane;
+    if (r_first >= N) return;
+    const int r_last = min(r_first + 31, N - 1);
+    // inclusive offset of this lane's rank (lanes past N repeat the last one: they own nothing)
+    const uint32_t end = offsets[min(r, r_last)];
+    uint32_t id = 0, cnt = 0;
     uint2 rc = make_uint2(0, 0);
     if (r < N) {
         id = order[r];
         cnt = tiles[id];
-        if (cnt) { end = offsets[r]; rc = rect[id]; }
+        if (cnt) rc = rect[id];
     }
-    unsigned mask = __ballot_sync(kFull, cnt != 0);
-    while (mask) {
-        const int src = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const uint32_t gid = __shfl_sync(kFull, id, src);
-        const uint32_t gcnt = __shfl_sync(kFull, cnt, src);
-        const uint32_t gend = __shfl_sync(kFull, end, src);
-        const uint32_t rx = __shfl_sync(kFull, rc.x, src), ry = __shfl_sync(kFull, rc.y, src);
-        const uint32_t x0 = rx & 0xFFFF, w = (rx >> 16) - x0, y0 = ry & 0xFFFF;
-        const uint32_t base = gend - gcnt;
-        for (uint32_t t = lane; t < gcnt; t += 32) {
-            const uint32_t yy = t / w, xx = t - yy * w;              // row-major: y outer, x inner
-            if (base + t < cap) {                                    // speculative mode: never write past the hint
-                keys[base + t] = (KeyT)((y0 + yy) * Tx + x0 + xx);
-                vals[base + t] = gid;
-            }
+    const uint32_t base = end - cnt;                               // exclusive offset of this lane's Gaussian
+    const uint32_t B = __shfl_sync(kFull, base, 0);
+    const uint32_t E = __shfl_sync(kFull, end, 31);
+    for (uint32_t p0 = B; p0 < E; p0 += 32) {
+        const uint32_t p = p0 + lane;
+        // owner = number of lanes whose inclusive offset is <= p (offsets are monotone)
+        int own = 0;
+#pragma unroll
+        for (int s = 16; s >= 1; s >>= 1) {
+            const uint32_t e = __shfl_sync(kFull, end, own + s - 1);
+            if (e <= p) own += s;
+        }
+        own = min(own, 31);
+        const uint32_t gbase = __shfl_sync(kFull, base, own);
+        const uint32_t gid = __shfl_sync(kFull, id, own);
+        const uint32_t rx = __shfl_sync(kFull, rc.x, own), ry = __shfl_sync(kFull, rc.y, own);
+        if (p < E && p < cap) {                                    // speculative mode: never write past the hint
+            const uint32_t x0 = rx & 0xFFFF, w = (rx >> 16) - x0, y0 = ry & 0xFFFF;
+            const uint32_t t = p - gbase;
+            const uint32_t yy = t / w, xx = t - yy * w;            // row-major: y outer, x inner
+            keys[p] = (KeyT)((y0 + yy) * Tx + x0 + xx);
+            vals[p] = gid;
         }
     }
 }
