@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TGS_ABI_VERSION 3
+#define TGS_ABI_VERSION 4
 
 #define TGS_EINVAL   (-1)   /* bad argument combination / shape */
 #define TGS_ENOMEM   (-2)   /* allocator callback returned NULL */
@@ -101,6 +101,8 @@ typedef struct TgsTouch {
     int32_t mode;          /* TGS_LOSS_* */
     int32_t row_begin;     /* pixel rows [row_begin,row_end) where the loss applies; (0,0) = every row.  A rank of the */
     int32_t row_end;       /* tile-row shard that renders a halo around its band restricts the loss to its own rows. */
+    const float* grad_scale; /* device scalar or NULL (= 1): upstream gradient of the touch-loss scalar, multiplied into
+                              * the fused gradient on the device (loss scaling, gradient accumulation, GradScaler) */
 } TgsTouch;
 
 /* Saved state handed from forward to backward. */
@@ -217,6 +219,15 @@ int tgs_backward(const TgsSettings* s, const TgsGaussians* g, const TgsSaved* sa
  */
 int tgs_touch_loss_scale(const float* target, int64_t num_pixels, float mult, float norm,
                          float* scale_out, void* stream);
+
+/*
+ * Value of the fused touch loss, for logging and for callers that want it as a term of their autograd graph:
+ * loss_out[0] = scale[0] * sum over pixel rows [row_begin,row_end) ((0,0) = all) of weight*|residual| (L1) or
+ * weight*residual^2 (L2); residual as written by tgs_forward (0 where the pixel is invalid), weight NULL = 1.
+ * acc: 8 bytes of device workspace (a double).
+ */
+int tgs_touch_loss_value(const float* residual, const float* weight, int32_t W, int32_t H, int32_t row_begin,
+                         int32_t row_end, int32_t mode, const float* scale, double* acc, float* loss_out, void* stream);
 
 /*
  * SURVEY §8(f) N2 -- the per-pixel part of the reference's touch / vision depth fusion, fp64, bit-identical
@@ -379,13 +390,17 @@ typedef struct TgsDensifyConfig {
     float cull_scale_thresh;  /* cull when max world scale > this (0.5) */
     float split_shrink;       /* split samples get scale / this (1.6) */
     int32_t n_split_samples;  /* 2 */
+    float split_screen_radius; /* > 0: split when the largest screen radius (pixels) since the last refine exceeds this */
+    float cull_screen_radius;  /* > 0: cull when it exceeds this */
 } TgsDensifyConfig;
 typedef struct TgsParamSet { float* means; float* shs; float* opacity; float* scales; float* quats; } TgsParamSet;
 size_t tgs_densify_temp_bytes(int32_t N);
 /* counts[i] (bit 31 = split) / offsets[i] (exclusive scan) of the outputs of Gaussian i: culled 0, kept 1,
- * duplicated 2 (itself, copy), split n_split_samples (the original is dropped).  Synchronises to return the total. */
+ * duplicated 2 (itself, copy), split n_split_samples (the original is dropped).  Synchronises to return the total.
+ * N == 0 is legal (total 0). */
 int tgs_densify_plan(int32_t N, const float* opacity_logit, const float* scales_log, const float* grad_accum,
-                     const int32_t* vis_count, const TgsDensifyConfig* cfg, int32_t allow_split_dup,
+                     const int32_t* vis_count, const int32_t* max_radii /* NULL: no screen-size rules */,
+                     const TgsDensifyConfig* cfg, int32_t allow_split_dup,
                      uint32_t* counts, uint32_t* offsets, void* temp, size_t temp_bytes,
                      int64_t* total_host, void* stream);
 /* in_pmv / out_pmv: 3 TgsParamSet each = (values, exp_avg, exp_avg_sq); raw parameters (opacity logit [N],

@@ -96,6 +96,8 @@ class DensifyConfig(NamedTuple):
     cull_scale_thresh: float = 0.5
     n_split_samples: int = 2
     split_shrink: float = 1.6
+    split_screen_radius: float = 0.0   # pixels; > 0: split when the largest screen radius since the last refine exceeds it
+    cull_screen_radius: float = 0.0    # pixels; > 0: cull when it exceeds it
 
 
 def densify_stats_reference(dmeans2D, radii, grad_accum, vis_count, max_radii):
@@ -107,7 +109,7 @@ def densify_stats_reference(dmeans2D, radii, grad_accum, vis_count, max_radii):
 
 
 def densify_reference(means, shs, opacity_logit, scales_log, quats, grad_accum, vis_count, noise, cfg: DensifyConfig,
-                      allow_split_dup: bool = True):
+                      allow_split_dup: bool = True, max_radii=None):
     """One refine step.  Output ORDER (ours; the trainer's is not in the tree): Gaussians in id order, each
     replaced by its outputs -- culled: nothing; kept: itself; duplicated: itself then its copy; split: its
     ``n_split_samples`` samples (the original is dropped).  Returns the new parameter tensors plus, per output,
@@ -118,9 +120,13 @@ def densify_reference(means, shs, opacity_logit, scales_log, quats, grad_accum, 
     avg = torch.where(vis_count > 0, avg, torch.zeros_like(avg))
     smax = torch.exp(scales_log).max(dim=-1).values
     high = (avg > cfg.grad_thresh) & allow_split_dup
-    split = high & (smax > cfg.size_thresh)
+    rmax = max_radii.to(avg.dtype) if max_radii is not None else torch.zeros_like(avg)
+    big = (rmax > cfg.split_screen_radius) & (cfg.split_screen_radius > 0) & allow_split_dup
+    split = (high & (smax > cfg.size_thresh)) | big
     dup = high & ~split
     cull = (torch.sigmoid(opacity_logit.reshape(-1)) < cfg.cull_alpha_thresh) | (smax > cfg.cull_scale_thresh)
+    if cfg.cull_screen_radius > 0:
+        cull = cull | (rmax > cfg.cull_screen_radius)
     split, dup = split & ~cull, dup & ~cull
     ns = cfg.n_split_samples
     count = torch.where(cull, 0, torch.where(split, ns, torch.where(dup, 2, 1)))

@@ -42,12 +42,24 @@ def frac_outliers(a, b, rtol=1e-4, atol_rel=1e-4):
     return float(((a - b).abs() > tol).double().mean())
 
 
+PARITY_LOG = []      # (test id, tensor name, rel_inf, outlier fraction or None, branch) -- printed by conftest's summary
+
+
 def assert_close_tensor(a, b, name, rel=1e-4, max_outlier_frac=0.0, outlier_rtol=1e-4):
     """The float-parity bar (north star: 1e-4 rel).  Per tensor: ||a-b||_inf / ||b||_inf <= rel, OR
-    (for image-like tensors where a 1-ulp difference in exp() can flip an alpha >= 1/255 / T < 1e-4
-    decision and move one pixel by ~1/255) at most `max_outlier_frac` of the elements off."""
+    (only where the call site grants an outlier budget: a 1-ulp difference between ex2.approx and expf can flip an
+    alpha >= 1/255 / T < 1e-4 decision of a (pixel, splat) pair sitting exactly on the threshold, which moves one
+    pixel by ~1/255 and the gradients of the splats behind it) at most `max_outlier_frac` of the elements off by
+    more than outlier_rtol*|b| + rel*max|b|.  Every call is logged with the branch that passed; the pytest terminal
+    summary prints the table (and writes gpurun_out/parity_report.json), so the slack actually used is visible."""
+    import os
     r = rel_inf(a, b)
+    test = os.environ.get("PYTEST_CURRENT_TEST", "").split(" ")[0]
     if r <= rel:
+        PARITY_LOG.append(dict(test=test, tensor=name, rel_inf=r, outlier_frac=None, branch="rel_inf", rel=rel))
         return
     f = frac_outliers(a, b, outlier_rtol, rel)
-    assert f <= max_outlier_frac, f"{name}: rel_inf={r:.3e} > {rel:g} and outlier fraction {f:.3e} > {max_outlier_frac:g}"
+    ok = f <= max_outlier_frac
+    PARITY_LOG.append(dict(test=test, tensor=name, rel_inf=r, outlier_frac=f, branch="outlier_budget" if ok else "FAIL",
+                           rel=rel, budget=max_outlier_frac))
+    assert ok, f"{name}: rel_inf={r:.3e} > {rel:g} and outlier fraction {f:.3e} > {max_outlier_frac:g}"

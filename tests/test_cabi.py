@@ -124,9 +124,15 @@ def test_new_entry_points_validate_arguments_without_gpu(tgs_lib):
     cfg = L.TgsDensifyConfig(grad_thresh=2e-4, size_thresh=0.01, cull_alpha_thresh=0.1, cull_scale_thresh=0.5,
                              split_shrink=1.6, n_split_samples=99)
     tot = C.c_int64(0)
-    assert lib.tgs_densify_plan(0, None, None, None, None, C.byref(cfg), 1, None, None, None, 0, C.byref(tot), None) == -1
-    assert lib.tgs_densify_plan(8, 0x1000, 0x1000, 0x1000, 0x1000, C.byref(cfg), 1, 0x1000, 0x1000, 0x1000, 1024,
+    tot.value = 7
+    assert lib.tgs_densify_plan(0, None, None, None, None, None, C.byref(cfg), 1, None, None, None, 0, C.byref(tot), None) == 0
+    assert tot.value == 0                                                                      # empty population stays empty
+    assert lib.tgs_densify_plan(-1, None, None, None, None, None, C.byref(cfg), 1, None, None, None, 0, C.byref(tot), None) == -1
+    assert lib.tgs_densify_plan(8, None, None, None, None, None, C.byref(cfg), 1, None, None, None, 0, C.byref(tot), None) == -1
+    assert lib.tgs_densify_plan(8, 0x1000, 0x1000, 0x1000, 0x1000, None, C.byref(cfg), 1, 0x1000, 0x1000, 0x1000, 1024,
                                 C.byref(tot), None) == -1 and b"n_split_samples" in lib.tgs_last_error()
+    assert lib.tgs_touch_loss_value(None, None, 8, 8, 0, 0, 1, None, None, None, None) == -1
+    assert lib.tgs_touch_loss_value(0x1000, None, 8, 8, 0, 0, 7, 0x1000, 0x1000, 0x1000, None) == -1 and b"bad mode" in lib.tgs_last_error()
     assert lib.tgs_densify_temp_bytes(1000) >= 256
     s = L.TgsSettings(image_width=64, image_height=64, tanfovx=0.5, tanfovy=0.5, scale_modifier=1.0)
     gg = L.TgsGaussians(N=4)

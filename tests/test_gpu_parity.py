@@ -216,6 +216,63 @@ def test_backward_parity(name, mode):
     assert torch.isfinite(got["means2D"]).all()
 
 
+def test_touch_loss_honours_the_upstream_gradient():
+    """the fused touch gradient must scale with whatever autograd carries.  (a) return_touch_loss=True:
+    the sixth output is the differentiable loss value; (0.37 * (photo + touch)).backward() matches the oracle's
+    0.37-scaled objective, and leaving the scalar out of the objective switches the fused gradient off.
+    (b) injected mode with an explicit loss_grad_scale (GradScaler / accumulation)."""
+    c, sc, cam = _case("c1")
+    H, W = c["H"], c["W"]
+    g = torch.Generator().manual_seed(17)
+    grgb = torch.rand(3, H, W, generator=g) / (3 * H * W)
+    tgt, wgt = _touch_inputs(sc, cam, c["deg"], 2)
+    touch = dict(touch_depth=tgt, touch_weight=wgt, depth_loss="l1", depth_loss_mult=0.2)
+    S = oracle_settings(cam, c["deg"])
+    names = ("means3D", "scales", "rotations", "opacities", "shs")
+
+    def oracle(scale_all, with_touch=True):
+        ins = {k: getattr(sc, k).clone().requires_grad_(True) for k in names}
+        out = O.rasterize(ins["means3D"], ins["opacities"], S, shs=ins["shs"], scales=ins["scales"],
+                          rotations=ins["rotations"], **touch)
+        loss = (out.color * grgb).sum() + (out.touch_loss if with_touch else 0.0)
+        (scale_all * loss).backward()
+        return out, {k: v.grad for k, v in ins.items()}
+
+    def cuda(scale_all, mode):
+        rs = cuda_settings(cam, c["deg"], DEV)
+        ins = {k: getattr(sc, k).to(DEV).clone().requires_grad_(True) for k in names}
+        tk = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in touch.items()}
+        ras = T.GaussianRasterizer(rs)
+        kw = dict(shs=ins["shs"], scales=ins["scales"], rotations=ins["rotations"])
+        if mode == "returned":
+            color, _, _, _, _, tl = ras(ins["means3D"], None, ins["opacities"], **kw, **tk, return_touch_loss=True)
+            (scale_all * ((color * grgb.to(DEV)).sum() + tl)).backward()
+        elif mode == "left_out":
+            color, _, _, _, _, tl = ras(ins["means3D"], None, ins["opacities"], **kw, **tk, return_touch_loss=True)
+            (scale_all * (color * grgb.to(DEV)).sum()).backward()
+        else:
+            out = ras(ins["means3D"], None, ins["opacities"], **kw, **tk,
+                      loss_grad_scale=torch.tensor(scale_all, device=DEV))
+            assert len(out) == 5
+            tl = None
+            (scale_all * (out[0] * grgb.to(DEV)).sum()).backward()
+        return tl, {k: v.grad.cpu() for k, v in ins.items()}
+
+    ref_out, ref = oracle(0.37)
+    tl, got = cuda(0.37, "returned")
+    assert abs(float(tl) - float(ref_out.touch_loss)) <= 1e-4 * abs(float(ref_out.touch_loss)) + 1e-9
+    for k in names:
+        assert_close_tensor(got[k], ref[k], "grad_" + k + " (returned touch loss x0.37)", 1e-4, 2e-3, 5e-3)
+    _, got = cuda(0.37, "injected")
+    for k in names:
+        assert_close_tensor(got[k], ref[k], "grad_" + k + " (loss_grad_scale 0.37)", 1e-4, 2e-3, 5e-3)
+    _, ref0 = oracle(0.37, with_touch=False)
+    _, got = cuda(0.37, "left_out")
+    for k in names:
+        assert_close_tensor(got[k], ref0[k], "grad_" + k + " (touch loss left out)", 1e-4, 2e-3, 5e-3)
+    assert rel_inf(ref0["means3D"], ref["means3D"]) > 1e-2, "the touch term must matter in this scene"
+
+
 def test_backward_precomputed_colors_and_cov():
     c, sc, cam = _case("c1")
     H, W = c["H"], c["W"]

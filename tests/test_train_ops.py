@@ -110,8 +110,8 @@ def test_adam_matches_torch_optim():
         assert rel_inf(a[:, :1], b0) < 2e-6 and rel_inf(a[:, 1:], b1) < 2e-6, nm
 
 
-@pytest.mark.parametrize("allow", [True, False])
-def test_densify_matches_oracle(allow):
+@pytest.mark.parametrize("allow,screen", [(True, False), (False, False), (True, True)])
+def test_densify_matches_oracle(allow, screen):
     g = torch.Generator().manual_seed(6)
     N, K = 3001, 16
     means, shs = torch.randn(N, 3, generator=g), torch.randn(N, K, 3, generator=g)
@@ -122,12 +122,17 @@ def test_densify_matches_oracle(allow):
     acc = torch.rand(N, generator=g) * 8e-4
     vc = torch.randint(0, 4, (N,), generator=g).int()
     noise = torch.randn(N, 2, 3, generator=g)
-    ref = TO.densify_reference(means, shs, op, sl, q, acc, vc, noise, TO.DensifyConfig(), allow_split_dup=allow)
+    # screen-size rules (largest screen radius since the last refine): split above 40 px, cull above 90 px
+    mr = torch.randint(0, 120, (N,), generator=g).int() if screen else None
+    ocfg = TO.DensifyConfig(split_screen_radius=40.0, cull_screen_radius=90.0) if screen else TO.DensifyConfig()
+    tcfg = T.TrainConfig(split_screen_radius=40.0, cull_screen_radius=90.0) if screen else T.TrainConfig()
+    ref = TO.densify_reference(means, shs, op, sl, q, acc, vc, noise, ocfg, allow_split_dup=allow, max_radii=mr)
     params = dict(means=means, shs=shs, opacity_logit=op, scales_log=sl, quats=q)
     params = {k: v.to(DEV) for k, v in params.items()}
     m = {k: torch.randn(v.shape, generator=g).to(DEV) for k, v in params.items()}
     v = {k: torch.rand(x.shape, generator=g).to(DEV) for k, x in params.items()}
-    np_, nm, nv, src = T.densify(params, m, v, acc.to(DEV), vc.to(DEV), noise.to(DEV), T.TrainConfig(), allow)
+    np_, nm, nv, src = T.densify(params, m, v, acc.to(DEV), vc.to(DEV), noise.to(DEV), tcfg, allow,
+                                 None if mr is None else mr.to(DEV))
     M = ref["means"].shape[0]
     assert np_["means"].shape[0] == M
     rsrc, rnew = ref["src"], ref["is_new"]
@@ -141,6 +146,22 @@ def test_densify_matches_oracle(allow):
         # Adam moments travel with carried-over Gaussians and are zero for new ones
         assert torch.equal(nm[k].cpu()[kept], m[k].cpu()[rsrc[kept]]) and torch.equal(nv[k].cpu()[kept], v[k].cpu()[rsrc[kept]])
         assert float(nm[k].cpu()[rnew].abs().sum()) == 0.0 and float(nv[k].cpu()[rnew].abs().sum()) == 0.0
+
+
+def test_densify_everything_culled_and_empty_population():
+    """refine may cull every Gaussian (M == 0); the next plan / step on the empty population must not raise."""
+    N, K = 64, 4
+    params = dict(means=torch.zeros(N, 3), shs=torch.zeros(N, K, 3), opacity_logit=torch.full((N,), -9.0),
+                  scales_log=torch.full((N, 3), -4.0), quats=torch.ones(N, 4))
+    params = {k: v.to(DEV) for k, v in params.items()}
+    m = {k: torch.zeros_like(v) for k, v in params.items()}
+    v = {k: torch.zeros_like(x) for k, x in params.items()}
+    z = torch.zeros(N, device=DEV)
+    p2, m2, v2, src = T.densify(params, m, v, z, z.int(), torch.zeros(N, 2, 3, device=DEV), T.TrainConfig(), True)
+    assert p2["means"].shape[0] == 0 and src.numel() == 0
+    e = torch.zeros(0, device=DEV)
+    p3, _, _, src3 = T.densify(p2, m2, v2, e, e.int(), torch.zeros(0, 2, 3, device=DEV), T.TrainConfig(), True)
+    assert p3["means"].shape[0] == 0 and src3.numel() == 0
 
 
 def test_densify_stats_matches_oracle():

@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TGS_LIB_PATH") or os.path.join(HERE, "libtgs.so")   # override: A/B builds
 
-TGS_ABI_VERSION = 3
+TGS_ABI_VERSION = 4
 BUF_GEOM, BUF_BINNING, BUF_IMAGE, BUF_TEMP = 0, 1, 2, 3
 LOSS_NONE, LOSS_L1, LOSS_L2 = 0, 1, 2
 LOSS_MODES = {"none": LOSS_NONE, "l1": LOSS_L1, "l2": LOSS_L2}
@@ -43,7 +43,7 @@ class TgsGaussians(C.Structure):
 
 class TgsTouch(C.Structure):
     _fields_ = [("target", c_fp), ("weight", c_fp), ("scale", c_fp), ("mode", C.c_int32),
-                ("row_begin", C.c_int32), ("row_end", C.c_int32)]
+                ("row_begin", C.c_int32), ("row_end", C.c_int32), ("grad_scale", c_fp)]
 
 
 class TgsSaved(C.Structure):
@@ -87,7 +87,8 @@ class TgsAdamGroup(C.Structure):
 
 class TgsDensifyConfig(C.Structure):
     _fields_ = [("grad_thresh", C.c_float), ("size_thresh", C.c_float), ("cull_alpha_thresh", C.c_float),
-                ("cull_scale_thresh", C.c_float), ("split_shrink", C.c_float), ("n_split_samples", C.c_int32)]
+                ("cull_scale_thresh", C.c_float), ("split_shrink", C.c_float), ("n_split_samples", C.c_int32),
+                ("split_screen_radius", C.c_float), ("cull_screen_radius", C.c_float)]
 
 
 class TgsParamSet(C.Structure):
@@ -118,6 +119,8 @@ SIGNATURES = {
     "tgs_backward": (C.c_int, [C.POINTER(TgsSettings), C.POINTER(TgsGaussians), C.POINTER(TgsSaved), c_fp,
                                c_fp, c_fp, c_fp, C.POINTER(TgsTouch), c_fp, c_fp, C.POINTER(TgsGrads), c_fp]),
     "tgs_touch_loss_scale": (C.c_int, [c_fp, C.c_int64, C.c_float, C.c_float, c_fp, c_fp]),
+    "tgs_touch_loss_value": (C.c_int, [c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_fp, c_fp, c_fp,
+                                       c_fp]),
     "tgs_fuse_touch_vision": (C.c_int, [c_fp, c_fp, c_fp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_int32,
                                         C.c_double, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "tgs_train_step_host": (C.c_int, [C.POINTER(TgsSettings), C.POINTER(TgsGaussians), c_fp, c_fp, c_fp,
@@ -136,7 +139,7 @@ SIGNATURES = {
     "tgs_adam_step": (C.c_int, [C.POINTER(TgsAdamGroup), C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, c_fp]),
     "tgs_densify_stats": (C.c_int, [C.c_int32, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "tgs_densify_temp_bytes": (C.c_size_t, [C.c_int32]),
-    "tgs_densify_plan": (C.c_int, [C.c_int32, c_fp, c_fp, c_fp, c_fp, C.POINTER(TgsDensifyConfig), C.c_int32,
+    "tgs_densify_plan": (C.c_int, [C.c_int32, c_fp, c_fp, c_fp, c_fp, c_fp, C.POINTER(TgsDensifyConfig), C.c_int32,
                                    c_fp, c_fp, c_fp, C.c_size_t, C.POINTER(C.c_int64), c_fp]),
     "tgs_densify_apply": (C.c_int, [C.c_int32, C.c_int32, c_fp, c_fp, c_fp, C.POINTER(TgsDensifyConfig),
                                     C.POINTER(TgsParamSet), C.POINTER(TgsParamSet), c_fp, c_fp]),

@@ -328,3 +328,14 @@ extern "C" int tgs_touch_loss_scale(const float* target, int64_t num_pixels, flo
     if (!scale_out || (norm <= 0.0f && num_pixels > 0 && !target)) { tgs_set_error("tgs_touch_loss_scale: bad arguments"); return TGS_EINVAL; }
     return tgs_launch_loss_scale(target, num_pixels, mult, norm, scale_out, (cudaStream_t)stream);
 }
+
+extern "C" int tgs_touch_loss_value(const float* residual, const float* weight, int32_t W, int32_t H, int32_t row_begin,
+                                    int32_t row_end, int32_t mode, const float* scale, double* acc, float* loss_out,
+                                    void* stream) {
+    if (!residual || !scale || !acc || !loss_out || W <= 0 || H <= 0) { tgs_set_error("tgs_touch_loss_value: bad arguments"); return TGS_EINVAL; }
+    if (mode != TGS_LOSS_NONE && mode != TGS_LOSS_L1 && mode != TGS_LOSS_L2) { tgs_set_error("tgs_touch_loss_value: bad mode %d", mode); return TGS_EINVAL; }
+    int r0 = 0, r1 = H;
+    if (row_end > row_begin) { r0 = row_begin < 0 ? 0 : row_begin; r1 = row_end > H ? H : row_end; }
+    return tgs_launch_touch_loss_value(residual, weight, (int64_t)r0 * W, (int64_t)r1 * W, mode, scale, acc, loss_out,
+                                       (cudaStream_t)stream);
+}

@@ -96,6 +96,10 @@ __device__ __forceinline__ bool patch_may_touch(const float4 a, const float4 q, 
     const float ex0 = pm.x0 - a.x, ex1 = pm.x1 - a.x, ey0 = pm.y0 - a.y, ey1 = pm.y1 - a.y;
     if (ex0 <= 0.0f && ex1 >= 0.0f && ey0 <= 0.0f && ey1 >= 0.0f) return thr <= 0.05f;
     const float A = q.x, B = q.y, Cc = q.z;
+    // the closed-form bound below assumes a convex quadratic; fp32 cancellation in det = a*c - b*b of an extremely
+    // anisotropic splat can leave an indefinite conic, for which nothing may be culled (forward and backward use
+    // different patch sizes and must still agree on every blended pair)
+    if (!(A > 0.0f) || !(A * Cc > B * B)) return true;
     const float rA = __fdividef(1.0f, A), rC = __fdividef(1.0f, Cc);
     float qmin, tmax;
     {   // vertical edges: dx fixed, dy* = clamp(-B dx / C)
@@ -254,7 +258,8 @@ k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
              const uint32_t* __restrict__ n_contrib, const float* __restrict__ depth_raw,
              const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
              const float* __restrict__ dL_dalpha, const float* __restrict__ t_target,
-             const float* __restrict__ t_weight, const float* __restrict__ t_scale, int t_mode,
+             const float* __restrict__ t_weight, const float* __restrict__ t_scale,
+             const float* __restrict__ t_gscale, int t_mode,
              int t_row0, int t_row1, float* __restrict__ residual, float* __restrict__ sgrad) {
     __shared__ __align__(128) float4 sbuf[2][kBwdBatch * 3];
     __shared__ __align__(8) uint64_t full[2];
@@ -276,7 +281,10 @@ k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
     uint32_t nc[kPix];
     uint32_t wmax = 0;
     const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
-    const float tscale = (t_target != nullptr && t_mode != TGS_LOSS_NONE) ? t_scale[0] : 0.0f;
+    // loss scale (mult / Z) times the upstream gradient of the touch-loss scalar (NULL = 1: the loss enters the
+    // caller's objective with unit weight)
+    const float tscale = (t_target != nullptr && t_mode != TGS_LOSS_NONE)
+                             ? t_scale[0] * (t_gscale ? t_gscale[0] : 1.0f) : 0.0f;
 #pragma unroll
     for (int r = 0; r < kPix; ++r) {
         const int py = py0 + r;
@@ -431,9 +439,39 @@ __global__ void k_finish_scale(float mult, float norm, float* out) {
     out[0] = mult / Z;
 }
 
+// value of the fused touch loss from the residual image (0 where invalid): scale * sum w*|r| (l1) or w*r^2 (l2)
+__global__ void k_touch_loss_value(const float* __restrict__ residual, const float* __restrict__ weight, int64_t i0,
+                                   int64_t i1, int mode, double* __restrict__ acc) {
+    int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    float s = 0.0f;
+    for (; i < i1; i += stride) {
+        const float r = residual[i], w = weight ? weight[i] : 1.0f;
+        s += (mode == TGS_LOSS_L1) ? w * fabsf(r) : w * r * r;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+    if ((threadIdx.x & 31) == 0 && s != 0.0f) atomicAdd(acc, (double)s);
+}
+__global__ void k_touch_loss_finish(const double* acc, const float* scale, float* out) { out[0] = (float)(acc[0] * (double)scale[0]); }
+
 }  // namespace
 
-
+int tgs_launch_touch_loss_value(const float* residual, const float* weight, int64_t i0, int64_t i1, int mode,
+                                const float* scale, double* acc, float* out, cudaStream_t st) {
+    TgsProfScope prof(TGS_STAGE_LOSS_SCALE, st);
+    TGS_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), st));
+    if (i1 > i0 && mode != TGS_LOSS_NONE) {
+        int blocks = (int)((i1 - i0 + 256 * 8 - 1) / (256 * 8));
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        k_touch_loss_value<<<blocks, 256, 0, st>>>(residual, weight, i0, i1, mode, acc);
+        tgs_count_own(1);
+    }
+    k_touch_loss_finish<<<1, 1, 0, st>>>(acc, scale, out);
+    tgs_count_own(1);
+    TGS_CUDA(cudaGetLastError());
+    return 0;
+}
 
 int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, BinView bv, ImageView iv,
                           float* out_color, float* out_depth, float* out_alpha,
@@ -454,17 +492,18 @@ int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, BinView bv, I
                           const TgsTouch* touch, float* residual, float* screen_grads, cudaStream_t st) {
     int nt = cam.Tx * (cam.row1 - cam.row0);
     if (nt <= 0) return 0;
-    const float* tt = nullptr; const float* tw = nullptr; const float* ts = nullptr; int mode = TGS_LOSS_NONE;
+    const float* tt = nullptr; const float* tw = nullptr; const float* ts = nullptr; const float* tg = nullptr;
+    int mode = TGS_LOSS_NONE;
     int tr0 = 0, tr1 = cam.H;
     if (touch && touch->target) {
-        tt = touch->target; tw = touch->weight; ts = touch->scale; mode = touch->mode;
+        tt = touch->target; tw = touch->weight; ts = touch->scale; tg = touch->grad_scale; mode = touch->mode;
         if (touch->row_end > touch->row_begin) { tr0 = touch->row_begin; tr1 = touch->row_end; }
         if (mode != TGS_LOSS_NONE && ts == nullptr) { tgs_set_error("touch loss enabled but scale pointer is NULL"); return TGS_EINVAL; }
     }
     TgsProfScope prof(TGS_STAGE_RENDER_BWD, st);
     k_render_bwd<<<2 * nt, kBwdThreads, 0, st>>>(bv.ranges, bv.records, cam.W, cam.H, cam.Tx, cam.row0, s->bg,
                                      s->depth_normalize, cam.alpha_max, iv.final_T, iv.n_contrib, iv.depth_raw, dL_dcolor,
-                                     dL_ddepth, dL_dalpha, tt, tw, ts, mode, tr0, tr1, residual, screen_grads);
+                                     dL_ddepth, dL_dalpha, tt, tw, ts, tg, mode, tr0, tr1, residual, screen_grads);
     tgs_count_own(1);
     TGS_KERNEL_CHECK(st, s->debug);
     return 0;

@@ -100,6 +100,8 @@ int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, BinView bv, I
                           const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
                           const TgsTouch* touch, float* residual, float* screen_grads, cudaStream_t st);
 int tgs_launch_loss_scale(const float* target, int64_t P, float mult, float norm, float* out, cudaStream_t st);
+int tgs_launch_touch_loss_value(const float* residual, const float* weight, int64_t i0, int64_t i1, int mode,
+                                const float* scale, double* acc, float* out, cudaStream_t st);
 
 static inline TgsCam tgs_make_cam(const TgsSettings* s) {
     TgsCam c;

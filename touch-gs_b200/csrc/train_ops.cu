@@ -304,21 +304,27 @@ k_densify_stats(int N, const float* __restrict__ dmeans2D, const int32_t* __rest
 
 __global__ void __launch_bounds__(256)
 k_densify_classify(int N, const float* __restrict__ opacity_logit, const float* __restrict__ scales_log,
-                   const float* __restrict__ grad_accum, const int32_t* __restrict__ vis_count, TgsDensifyConfig cfg,
-                   int allow, uint32_t* __restrict__ counts) {
+                   const float* __restrict__ grad_accum, const int32_t* __restrict__ vis_count,
+                   const int32_t* __restrict__ max_radii, TgsDensifyConfig cfg, int allow, uint32_t* __restrict__ counts) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= N) return;
     const int vc = vis_count[i];
     const float avg = vc > 0 ? grad_accum[i] / (float)vc : 0.0f;
     const float smax = fmaxf(fmaxf(expf(scales_log[3 * i]), expf(scales_log[3 * i + 1])), expf(scales_log[3 * i + 2]));
     const float op = 1.0f / (1.0f + expf(-opacity_logit[i]));
-    const bool cull = (op < cfg.cull_alpha_thresh) || (smax > cfg.cull_scale_thresh);
+    // screen-size rules (largest screen radius seen since the last refine; a threshold of 0 switches the rule off)
+    const float rmax = max_radii ? (float)max_radii[i] : 0.0f;
+    const bool big_screen = cfg.split_screen_radius > 0.0f && rmax > cfg.split_screen_radius;
+    const bool cull = (op < cfg.cull_alpha_thresh) || (smax > cfg.cull_scale_thresh) ||
+                      (cfg.cull_screen_radius > 0.0f && rmax > cfg.cull_screen_radius);
     const bool high = allow && (avg > cfg.grad_thresh);
+    const bool split = !cull && allow && ((high && smax > cfg.size_thresh) || big_screen);
     uint32_t c = 1;
     if (cull) c = 0;
-    else if (high) c = (smax > cfg.size_thresh) ? (uint32_t)cfg.n_split_samples : 2u;
+    else if (split) c = (uint32_t)cfg.n_split_samples;
+    else if (high) c = 2u;
     // bit 31 marks "split" so that apply does not have to recompute the classification
-    counts[i] = c | ((!cull && high && smax > cfg.size_thresh) ? 0x80000000u : 0u);
+    counts[i] = c | (split ? 0x80000000u : 0u);
 }
 
 struct CountOnly {
@@ -512,16 +518,18 @@ extern "C" size_t tgs_densify_temp_bytes(int32_t N) {
 }
 
 extern "C" int tgs_densify_plan(int32_t N, const float* opacity_logit, const float* scales_log, const float* grad_accum,
-                                const int32_t* vis_count, const TgsDensifyConfig* cfg, int32_t allow_split_dup,
+                                const int32_t* vis_count, const int32_t* max_radii, const TgsDensifyConfig* cfg,
+                                int32_t allow_split_dup,
                                 uint32_t* counts, uint32_t* offsets, void* temp, size_t temp_bytes,
                                 int64_t* total_host, void* stream) {
-    if (N <= 0 || !opacity_logit || !scales_log || !grad_accum || !vis_count || !cfg || !counts || !offsets || !temp || !total_host) {
+    if (N < 0 || !cfg || !total_host || (N > 0 && (!opacity_logit || !scales_log || !grad_accum || !vis_count || !counts || !offsets || !temp))) {
         tgs_set_error("tgs_densify_plan: bad arguments"); return TGS_EINVAL; }
+    if (N == 0) { *total_host = 0; return 0; }          // an empty population stays empty
     if (cfg->n_split_samples < 1 || cfg->n_split_samples > 8) { tgs_set_error("tgs_densify_plan: n_split_samples out of range"); return TGS_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
     TgsProfScope prof(TGS_STAGE_REFINE, st);
-    k_densify_classify<<<(N + 255) / 256, 256, 0, st>>>(N, opacity_logit, scales_log, grad_accum, vis_count, *cfg,
-                                                        allow_split_dup, counts);
+    k_densify_classify<<<(N + 255) / 256, 256, 0, st>>>(N, opacity_logit, scales_log, grad_accum, vis_count, max_radii,
+                                                        *cfg, allow_split_dup, counts);
     tgs_count_own(1);
     TGS_CUDA(cudaGetLastError());
     cub::TransformInputIterator<uint32_t, CountOnly, const uint32_t*> it(counts, CountOnly());
@@ -539,7 +547,8 @@ extern "C" int tgs_densify_plan(int32_t N, const float* opacity_logit, const flo
 extern "C" int tgs_densify_apply(int32_t N, int32_t K, const uint32_t* counts, const uint32_t* offsets,
                                  const float* noise, const TgsDensifyConfig* cfg, const TgsParamSet* in_pmv,
                                  const TgsParamSet* out_pmv, int32_t* src_out, void* stream) {
-    if (N <= 0 || K < 0 || !counts || !offsets || !cfg || !in_pmv || !out_pmv) { tgs_set_error("tgs_densify_apply: bad arguments"); return TGS_EINVAL; }
+    if (N < 0 || K < 0 || !cfg || !in_pmv || !out_pmv || (N > 0 && (!counts || !offsets))) { tgs_set_error("tgs_densify_apply: bad arguments"); return TGS_EINVAL; }
+    if (N == 0) return 0;
     const TgsParamSet& p = in_pmv[0]; const TgsParamSet& o = out_pmv[0];
     if (!p.means || !p.scales || !p.quats || !o.means || !o.scales || !o.quats || !noise) { tgs_set_error("tgs_densify_apply: means / scales / quats / noise required"); return TGS_EINVAL; }
     const int64_t threads = (int64_t)N * 32;

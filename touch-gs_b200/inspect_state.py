@@ -40,7 +40,7 @@ def forward_state(means3D, opacities, rs: GaussianRasterizationSettings, shs=Non
     ctx = Ctx()
     e = torch.empty(0, device=means3D.device)
     with torch.no_grad():
-        color, radii, depth, alpha, resid = _RasterizeGaussians.forward(
+        color, radii, depth, alpha, resid, _ = _RasterizeGaussians.forward(
             ctx, means3D, None, e if shs is None else shs, e if colors_precomp is None else colors_precomp,
             opacities, e if scales is None else scales, e if rotations is None else rotations,
             e if cov3D_precomp is None else cov3D_precomp, rs, opt)

@@ -58,6 +58,12 @@ class TouchOptions(NamedTuple):
     info: Optional[dict] = None                    # filled with num_rendered / capacity of the call
     touch_rows: Optional[Tuple[int, int]] = None   # pixel rows where the touch loss applies (None = all rows)
     peer_exchange: object = None                   # sharding.PeerScreenGrads: fused P2P gather instead of all-reduce
+    return_touch_loss: bool = False                # True: the operator also returns the touch loss as a DIFFERENTIABLE
+                                                   # scalar; the fused gradient is then scaled by that scalar's upstream
+                                                   # gradient (0 if the caller leaves it out of the objective)
+    loss_grad_scale: object = None                 # injected mode (return_touch_loss=False): explicit upstream scale of
+                                                   # the objective (float or 0-dim tensor), e.g. a GradScaler's scale or
+                                                   # 1/accumulation_steps; None = 1
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -179,6 +185,16 @@ def _empty_on(device):
     return t
 
 
+_ZERO = {}
+
+
+def _zero_scalar(device):
+    t = _ZERO.get(device)
+    if t is None:
+        t = _ZERO[device] = torch.zeros((), dtype=torch.float32, device=device)
+    return t
+
+
 def _empty_if(t):
     return None if (t is None or t.numel() == 0) else t
 
@@ -251,6 +267,25 @@ class _RasterizeGaussians(torch.autograd.Function):
                     pass
             L.check(rc, "tgs_forward")
 
+            # scale = depth_loss_mult / Z and the VALUE of the fused touch loss (logging; differentiable on request)
+            tscale = None
+            tloss = None
+            if touch_depth is not None and opt.depth_loss != "none":
+                tscale = torch.empty(2, dtype=torch.float32, device=dev)
+                norm = float(opt.depth_loss_norm) if opt.depth_loss_norm is not None else 0.0
+                L.check(lib.tgs_touch_loss_scale(_ptr(touch_depth), H * W, float(opt.depth_loss_mult), norm,
+                                                 _ptr(tscale), _stream_ptr(dev)), "tgs_touch_loss_scale")
+                if opt.return_touch_loss:
+                    acc = torch.empty(1, dtype=torch.float64, device=dev)
+                    tloss = torch.empty((), dtype=torch.float32, device=dev)
+                    tr = (0, 0) if opt.touch_rows is None else (int(opt.touch_rows[0]), int(opt.touch_rows[1]))
+                    if opt.touch_rows is None and not full:      # a band without explicit loss rows: its own pixel rows
+                        tr = (min(r0 * TILE, H), min(r1 * TILE, H))
+                    L.check(lib.tgs_touch_loss_value(_ptr(resid), _ptr(touch_weight), W, H, tr[0], tr[1],
+                                                     L.LOSS_MODES[opt.depth_loss], _ptr(tscale), _ptr(acc), _ptr(tloss),
+                                                     _stream_ptr(dev)), "tgs_touch_loss_value")
+        ctx.tscale = tscale
+
         ctx.rs, ctx.opt, ctx.K = rs, opt, K
         ctx.settings, ctx.keep = s, keep           # the validated C structs are reused by backward
         ctx.opacity_shape = opacity_shape
@@ -269,11 +304,15 @@ class _RasterizeGaussians(torch.autograd.Function):
                               cov3Ds_precomp if cov3Ds_precomp is not None else none,
                               radii, scratch.bufs[L.BUF_GEOM], scratch.bufs[L.BUF_BINNING], scratch.bufs[L.BUF_IMAGE])
         ctx.set_materialize_grads(False)
-        ctx.mark_non_differentiable(radii, resid)
-        return color, radii, depth, alpha, resid
+        if tloss is None:
+            tloss = _zero_scalar(dev)                  # placeholder (cached: no fill kernel per call)
+            ctx.mark_non_differentiable(radii, resid, tloss)
+        else:
+            ctx.mark_non_differentiable(radii, resid)
+        return color, radii, depth, alpha, resid, tloss
 
     @staticmethod
-    def backward(ctx, g_color, _g_radii, g_depth, g_alpha, _g_resid):
+    def backward(ctx, g_color, _g_radii, g_depth, g_alpha, _g_resid, g_tloss=None):
         lib = L.load()
         (means3D, opacities, sh, colors, scales, rots, cov3D, radii, geom, binning, image) = ctx.saved_tensors
         has_sh, has_col, has_sr, has_cov = ctx.has
@@ -298,16 +337,28 @@ class _RasterizeGaussians(torch.autograd.Function):
             touch_depth, touch_weight = ctx.touch
             touch = None
             if touch_depth is not None and opt.depth_loss != "none":
-                scale = torch.empty(2, dtype=torch.float32, device=dev)
-                norm = float(opt.depth_loss_norm) if opt.depth_loss_norm is not None else 0.0
-                L.check(lib.tgs_touch_loss_scale(_ptr(touch_depth), H * W, float(opt.depth_loss_mult), norm,
-                                                 _ptr(scale), _stream_ptr(dev)), "tgs_touch_loss_scale")
-                keep.append(scale)
+                scale = ctx.tscale
+                # upstream gradient of the touch-loss scalar, applied on the device (no host sync):
+                #   return_touch_loss=True : whatever autograd carries for that output (None = the caller left the loss
+                #                            out of its objective -> the fused gradient is off for this backward);
+                #   injected mode          : 1, or the caller's explicit `loss_grad_scale`.
+                gs = None
+                mode = L.LOSS_MODES[opt.depth_loss]
+                if opt.return_touch_loss:
+                    if g_tloss is None:
+                        mode = L.LOSS_NONE
+                    else:
+                        gs = g_tloss.detach().reshape(1).to(device=dev, dtype=torch.float32).contiguous()
+                elif opt.loss_grad_scale is not None:
+                    gs = torch.as_tensor(opt.loss_grad_scale, dtype=torch.float32, device=dev).detach().reshape(1).contiguous()
+                if gs is not None:
+                    keep.append(gs)
                 touch = L.TgsTouch(target=touch_depth.data_ptr(),
                                    weight=None if touch_weight is None else touch_weight.data_ptr(),
-                                   scale=scale.data_ptr(), mode=L.LOSS_MODES[opt.depth_loss],
+                                   scale=scale.data_ptr(), mode=mode,
                                    row_begin=0 if opt.touch_rows is None else int(opt.touch_rows[0]),
-                                   row_end=0 if opt.touch_rows is None else int(opt.touch_rows[1]))
+                                   row_end=0 if opt.touch_rows is None else int(opt.touch_rows[1]),
+                                   grad_scale=None if gs is None else gs.data_ptr())
             peer = opt.peer_exchange if N > 0 else None
             if peer is not None and N > peer.capacity:
                 # more Gaussians than the peer-mapped buffers were sized for (the population grew at a refine step):
@@ -361,9 +412,11 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
                         cov3Ds_precomp, raster_settings, touch: Optional[TouchOptions] = None):
     """Same positional signature as the reference-era ``rasterize_gaussians`` plus the
     optional ``touch`` extension.  Returns (color [3,H,W], radii [N] int32, depth [1,H,W],
-    alpha [1,H,W], depth_residual [1,H,W])."""
-    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                     cov3Ds_precomp, raster_settings, touch)
+    alpha [1,H,W], depth_residual [1,H,W]) -- plus the differentiable touch-loss scalar as a sixth element when
+    ``touch.return_touch_loss`` is set."""
+    out = _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                    cov3Ds_precomp, raster_settings, touch)
+    return out if (touch is not None and touch.return_touch_loss) else out[:5]
 
 
 class GaussianRasterizer(torch.nn.Module):
@@ -391,7 +444,8 @@ class GaussianRasterizer(torch.nn.Module):
                 rotations=None, cov3D_precomp=None, *, touch_depth=None, touch_weight=None,
                 depth_loss: str = "none", depth_loss_mult: float = 1.0, depth_normalize: bool = True,
                 depth_loss_norm: Optional[float] = None, tile_rows=None, process_group=None,
-                rendered_hint: int = 0, touch_rows=None, peer_exchange=None):
+                rendered_hint: int = 0, touch_rows=None, peer_exchange=None, return_touch_loss: bool = False,
+                loss_grad_scale=None):
         if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
             raise Exception("Please provide excatly one of either SHs or precomputed colors!")
         if ((scales is None or rotations is None) and cov3D_precomp is None) or \
@@ -400,7 +454,8 @@ class GaussianRasterizer(torch.nn.Module):
         e = _empty_on(means3D.device)
         info = {}
         opt = TouchOptions(touch_depth, touch_weight, depth_loss, depth_loss_mult, depth_normalize,
-                           depth_loss_norm, tile_rows, process_group, rendered_hint, info, touch_rows, peer_exchange)
+                           depth_loss_norm, tile_rows, process_group, rendered_hint, info, touch_rows, peer_exchange,
+                           bool(return_touch_loss), loss_grad_scale)
         out = rasterize_gaussians(means3D, means2D,
                                   e if shs is None else shs, e if colors_precomp is None else colors_precomp,
                                   opacities, e if scales is None else scales, e if rotations is None else rotations,

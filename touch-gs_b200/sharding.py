@@ -126,11 +126,24 @@ class PeerScreenGrads:
 
 
 def make_peer_exchange(group, max_gaussians: int, device):
-    """PeerScreenGrads if symmetric memory works on this box (NVLink P2P between all ranks), else None (the caller
-    then uses the NCCL all-reduce path).  Both paths are GPU paths of this library; there is no CPU fallback."""
+    """PeerScreenGrads if symmetric memory works on EVERY rank of the group (NVLink P2P between all ranks), else None
+    (the caller then uses the NCCL all-reduce path).  The decision is collective: a MIN all-reduce of the per-rank
+    success flag, so a failure on some ranks cannot leave the others waiting in the peer barrier while those call
+    all_reduce.  Both paths are GPU paths of this library; there is no CPU fallback."""
+    import torch
+    import torch.distributed as dist
+    peer, err = None, None
     try:
-        return PeerScreenGrads(group, max_gaussians, device)
+        peer = PeerScreenGrads(group, max_gaussians, device)
     except Exception as e:  # noqa: BLE001
-        import warnings
-        warnings.warn(f"symmetric-memory peer exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduce")
-        return None
+        err = e
+    grp = group if group is not None else dist.group.WORLD
+    flag = torch.tensor([1 if peer is not None else 0], dtype=torch.int32,
+                        device=device if dist.get_backend(grp) == "nccl" else "cpu")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=grp)
+    if int(flag.item()) == 1:
+        return peer
+    import warnings
+    why = f"{type(err).__name__}: {err}" if err is not None else "a peer rank could not set it up"
+    warnings.warn(f"symmetric-memory peer exchange unavailable ({why}); every rank uses the NCCL all-reduce")
+    return None

@@ -171,6 +171,8 @@ class TrainConfig:
     cull_scale_thresh: float = 0.5
     n_split_samples: int = 2
     split_shrink: float = 1.6
+    split_screen_radius: float = 0.0             # pixels; > 0: split Gaussians whose largest screen radius since the last
+    cull_screen_radius: float = 0.0              # refine exceeds it / cull them (the screen-size rules; 0 = off)
     seed: int = 0
 
     def lr_means_at(self, step: int) -> float:
@@ -189,14 +191,15 @@ class TrainConfig:
     def densify_struct(self) -> "L.TgsDensifyConfig":
         return L.TgsDensifyConfig(grad_thresh=self.densify_grad_thresh, size_thresh=self.densify_size_thresh,
                                   cull_alpha_thresh=self.cull_alpha_thresh, cull_scale_thresh=self.cull_scale_thresh,
-                                  split_shrink=self.split_shrink, n_split_samples=self.n_split_samples)
+                                  split_shrink=self.split_shrink, n_split_samples=self.n_split_samples,
+                                  split_screen_radius=self.split_screen_radius, cull_screen_radius=self.cull_screen_radius)
 
 
 PARAM_NAMES = ("means", "shs", "opacity_logit", "scales_log", "quats")
 
 
 def densify(params: dict, exp_avg: dict, exp_avg_sq: dict, grad_accum, vis_count, noise, cfg: TrainConfig,
-            allow_split_dup: bool = True):
+            allow_split_dup: bool = True, max_radii=None):
     """One refine step on the raw parameter tensors + their Adam moments (stream compaction on the GPU).
     Returns (new_params, new_exp_avg, new_exp_avg_sq, src) -- see ``tgs_densify_apply`` for ``src``."""
     lib = L.load()
@@ -211,7 +214,8 @@ def densify(params: dict, exp_avg: dict, exp_avg_sq: dict, grad_accum, vis_count
         temp = torch.empty(tb, dtype=torch.uint8, device=dev)
         total = C.c_int64(0)
         L.check(lib.tgs_densify_plan(N, _ptr(params["opacity_logit"]), _ptr(params["scales_log"]), _ptr(grad_accum),
-                                     _ptr(vis_count), C.byref(dc), int(bool(allow_split_dup)), _ptr(counts), _ptr(offsets),
+                                     _ptr(vis_count), _ptr(max_radii), C.byref(dc), int(bool(allow_split_dup)), _ptr(counts),
+                                     _ptr(offsets),
                                      _ptr(temp), tb, C.byref(total), _stream_ptr(dev)), "tgs_densify_plan")
         M = int(total.value)
         widths = dict(means=(3,), shs=(K, 3), opacity_logit=tuple(params["opacity_logit"].shape[1:]), scales_log=(3,), quats=(4,))
@@ -353,7 +357,7 @@ class TouchGSTrainer:
         with torch.cuda.device(self.dev):
             noise = torch.randn((N, cfg.n_split_samples, 3), dtype=torch.float32, device=self.dev, generator=self.gen)
             self.p, self.m, self.v, src = densify(self.p, self.m, self.v, self.grad_accum, self.vis_count, noise, cfg,
-                                                  allow_split_dup)
+                                                  allow_split_dup, self.max_radii)
             self._reset_stats()
             self.hints.clear()
             if cfg.reset_alpha_every > 0 and self.step % (cfg.reset_alpha_every * cfg.refine_every) == 0:
