@@ -287,12 +287,20 @@ typedef struct TgsBinningLayout {
     size_t sort_temp;
     size_t sort_temp_bytes;
     size_t key_bytes;         /* 2 when T <= 65536, else 4 */
+    size_t ckpt;              /* float[slots][5][256]: per-pixel (T, r, g, b, D) composited BEFORE list position
+                               * ranges[tile].x + 256k, written by the forward for every 256-record boundary it crosses;
+                               * slot = that position >> 8 (unique per boundary).  Lets the backward replay a tile's list
+                               * in independent 256-record segments. */
+    size_t slot_tile;         /* uint32[slots]: tile that owns the boundary in this slot, 0xFFFFFFFF = none */
+    size_t work_counter;      /* uint32: dynamic work-unit counter of the backward */
+    size_t slots;             /* (I >> 8) + 2 */
     size_t total;
 } TgsBinningLayout;
 typedef struct TgsImageLayout {
     size_t final_T;        /* float[H,W] */
     size_t n_contrib;      /* uint32[H,W] */
     size_t depth_raw;      /* float[H,W] un-normalised sum depth*alpha*T */
+    size_t color_acc;      /* float[3,H,W] composited colour WITHOUT the background term */
     size_t total;
 } TgsImageLayout;
 int tgs_geom_layout(int32_t N, TgsGeomLayout* out);

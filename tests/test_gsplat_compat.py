@@ -80,7 +80,7 @@ def test_rasterize_and_gradients_match_oracle():
     assert_close_tensor(out, img.color.permute(1, 2, 0), "image", 1e-4, 5e-4)
     assert_close_tensor(alpha, img.alpha, "alpha", 1e-4, 5e-4)
     for nm, a, b in zip(("means3d", "scales", "quats", "colors", "opacity"), cin, ins):
-        assert_close_tensor(a.grad, b.grad, "v_" + nm, 1e-4, 2e-3, 1e-3)
+        assert_close_tensor(a.grad, b.grad, "v_" + nm, 1e-4)
 
 
 def test_depth_as_colour_and_single_channel():

@@ -60,7 +60,7 @@ def test_refstructure_matches_oracle(case):
     dhat = torch.where(alpha > 0, draw / alpha.clamp_min(1e-30), torch.zeros_like(draw))
     assert_close_tensor(dhat, ref.depth, "depth", 1e-4, 5e-4)
     for name, a, b in zip(("means3D", "opacities", "shs", "scales", "rotations"), cin, ins):
-        assert_close_tensor(a.grad, b.grad, "d" + name, 1e-4, 2e-3, 1e-3)
+        assert_close_tensor(a.grad, b.grad, "d" + name, 1e-4)
 
 
 def test_product_kernels_match_refstructure_at_full_size_c3():
@@ -101,4 +101,4 @@ def test_product_kernels_match_refstructure_at_full_size_c3():
     ((color_b - gt).abs().mean() + R.touch_depth_loss_unfused(draw, alpha, tgt, wgt, 0.2, "l1")).backward()
     for name, a, b in zip(("means3D", "opacities", "shs", "scales", "rotations"), a_in, b_in):
         assert torch.isfinite(a.grad).all()
-        assert_close_tensor(a.grad, b.grad, "d" + name, 1e-4, 1e-4, 1e-3)
+        assert_close_tensor(a.grad, b.grad, "d" + name, 1e-4)

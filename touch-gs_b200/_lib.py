@@ -67,11 +67,11 @@ class TgsGeomLayout(C.Structure):
 class TgsBinningLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in
                 ("ranges", "records", "tile_sorted", "vals_sorted", "tile_unsorted", "vals_unsorted",
-                 "sort_temp", "sort_temp_bytes", "key_bytes", "total")]
+                 "sort_temp", "sort_temp_bytes", "key_bytes", "ckpt", "slot_tile", "work_counter", "slots", "total")]
 
 
 class TgsImageLayout(C.Structure):
-    _fields_ = [(n, C.c_size_t) for n in ("final_T", "n_contrib", "depth_raw", "total")]
+    _fields_ = [(n, C.c_size_t) for n in ("final_T", "n_contrib", "depth_raw", "color_acc", "total")]
 
 
 class TgsRefBinningLayout(C.Structure):

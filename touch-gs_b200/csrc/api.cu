@@ -108,6 +108,10 @@ extern "C" int tgs_binning_layout(int64_t I, int32_t T, TgsBinningLayout* o) {
     o->vals_unsorted = c.take(n * sizeof(uint32_t));
     o->sort_temp_bytes = tgs_tile_sort_temp_bytes(I > 0 ? I : 1, T);
     o->sort_temp = c.take(o->sort_temp_bytes);
+    o->slots = (n >> 8) + 2;
+    o->ckpt = c.take(o->slots * TGS_CKPT_FLOATS * sizeof(float));
+    o->slot_tile = c.take(o->slots * sizeof(uint32_t));
+    o->work_counter = c.take(sizeof(uint32_t));
     o->total = c.off;
     return 0;
 }
@@ -116,6 +120,7 @@ extern "C" int tgs_image_layout(int32_t W, int32_t H, TgsImageLayout* o) {
     o->final_T = c.take(p * 4);
     o->n_contrib = c.take(p * 4);
     o->depth_raw = c.take(p * 4);
+    o->color_acc = c.take(p * 12);
     o->total = c.off;
     return 0;
 }
@@ -138,13 +143,15 @@ BinView tgs_bin_view(void* base, int64_t I, int T) {
     v.tile_sorted = b + l.tile_sorted; v.vals_sorted = (uint32_t*)(b + l.vals_sorted);
     v.tile_unsorted = b + l.tile_unsorted; v.vals_unsorted = (uint32_t*)(b + l.vals_unsorted);
     v.cub_temp = b + l.sort_temp; v.cub_temp_bytes = l.sort_temp_bytes;
+    v.ckpt = (float*)(b + l.ckpt); v.slot_tile = (uint32_t*)(b + l.slot_tile);
+    v.work_counter = (uint32_t*)(b + l.work_counter);
     return v;
 }
 ImageView tgs_image_view(void* base, int W, int H) {
     TgsImageLayout l; tgs_image_layout(W, H, &l);
     char* b = (char*)base; ImageView v;
     v.final_T = (float*)(b + l.final_T); v.n_contrib = (uint32_t*)(b + l.n_contrib);
-    v.depth_raw = (float*)(b + l.depth_raw);
+    v.depth_raw = (float*)(b + l.depth_raw); v.color_acc = (float*)(b + l.color_acc);
     return v;
 }
 
@@ -271,7 +278,8 @@ extern "C" int tgs_backward_render(const TgsSettings* s, const TgsGaussians* g, 
     BinView bv = tgs_bin_view(saved->binning, saved->capacity > 0 ? saved->capacity : saved->num_rendered, cam.Tx * cam.Ty);
     ImageView iv = tgs_image_view(saved->image, cam.W, cam.H);
     if (g->N > 0) TGS_CUDA(cudaMemsetAsync(screen_grads, 0, sizeof(float) * TGS_NGRAD * (size_t)g->N, st));
-    return tgs_launch_render_bwd(cam, s, bv, iv, dL_dcolor, dL_ddepth, dL_dalpha, touch, residual_out, screen_grads, st);
+    return tgs_launch_render_bwd(cam, s, bv, iv, saved->num_rendered, dL_dcolor, dL_ddepth, dL_dalpha, touch, residual_out,
+                                 screen_grads, st);
 }
 
 extern "C" int tgs_backward_preprocess(const TgsSettings* s, const TgsGaussians* g, const TgsSaved* saved,

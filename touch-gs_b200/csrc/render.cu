@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(256)
 k_render_fwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ recs, int W, int H, int Tx,
              int row0, const float* __restrict__ bg, int normalize, float alpha_max, float* __restrict__ out_color,
              float* __restrict__ out_depth, float* __restrict__ out_alpha, float* __restrict__ final_T,
-             uint32_t* __restrict__ n_contrib, float* __restrict__ depth_raw,
+             uint32_t* __restrict__ n_contrib, float* __restrict__ depth_raw, float* __restrict__ color_acc,
+             float* __restrict__ ckpt, uint32_t* __restrict__ slot_tile,
              const float* __restrict__ t_target, float* __restrict__ residual) {
     __shared__ __align__(128) float4 sbuf[2][kBatch * 3];
     __shared__ __align__(8) uint64_t full[2];
@@ -188,6 +189,14 @@ k_render_fwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
         const int nd = __syncthreads_count(done);
         if (nd == 256) break;
         if (tid == 0 && b + 2 < nb) issue(b + 2);
+        if (b + 1 < nb) {
+            // the list continues: CHECKPOINT the per-pixel state in front of list position (b+1)*256, so that the
+            // backward can replay the tile's list in independent 256-record segments (one warp per segment)
+            const uint32_t slot = (rng.x + (uint32_t)(b + 1) * kBatch) >> 8;   // unique per (tile, boundary)
+            float* ck = ckpt + (size_t)slot * TGS_CKPT_FLOATS + ((pm.py & 15) * 16 + (pm.px & 15));
+            ck[0] = T; ck[256] = C0; ck[512] = C1; ck[768] = C2; ck[1024] = D;
+            if (tid == 0) slot_tile[slot] = (uint32_t)tile;
+        }
     }
     // a copy issued for batch b+1 may still be in flight if we broke out early: the CTA must not
     // retire (and free its shared memory) before it lands.
@@ -198,6 +207,7 @@ k_render_fwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
         out_color[pm.pix] = C0 + T * bg[0];
         out_color[HW + pm.pix] = C1 + T * bg[1];
         out_color[2 * HW + pm.pix] = C2 + T * bg[2];
+        color_acc[pm.pix] = C0; color_acc[HW + pm.pix] = C1; color_acc[2 * HW + pm.pix] = C2;
         const float A = 1.0f - T;
         out_alpha[pm.pix] = A;
         const float dhat = normalize ? (A > 0.0f ? D / A : 0.0f) : D;
@@ -240,186 +250,240 @@ __device__ __forceinline__ void warp_reduce_scatter10(const float (&v)[TGS_NGRAD
     valid = !(lane & 1) && ((lane & 8) ? !(lane & 4) : !((lane & 4) && (lane & 2)));
 }
 
-// Backward: ONE SINGLE-WARP CTA PER 16x8 HALF TILE, FOUR PIXELS PER THREAD (a vertical strip x, y0..y0+3).
-// Measured at c3 (1M splats, 1080p): 5.16 M contributing (8x4 patch, splat) pairs but only 1.84 M
-// contributing (16x8 patch, splat) pairs, so the warp reduction + REDs -- a third of the work of the
-// one-pixel-per-thread kernel -- are paid 2.8x less often.  dx is shared by a thread's four pixels, so
-// the five geometric gradients and dL/dopacity collapse into three per-thread moments
+// Backward: ONE WARP PER (16x8 HALF TILE, 256-RECORD SEGMENT of the tile's list), FOUR PIXELS PER THREAD (a vertical
+// strip x, y0..y0+3).  Measured at c3 (1M splats, 1080p): 5.16 M contributing (8x4 patch, splat) pairs but only 1.84 M
+// contributing (16x8 patch, splat) pairs, so the warp reduction + REDs -- a third of the work of a one-pixel-per-thread
+// kernel -- are paid 2.8x less often.  dx is shared by a thread's four pixels, so the five geometric gradients and
+// dL/dopacity collapse into three per-thread moments
 //   U0 = sum u,  U1 = sum u*dy,  U2 = sum u*dy^2     with u = o*G*dL/dalpha
 // from which  d/dx = -(A dx U0 + B U1), d/dy = -(C U1 + B dx U0), dA = -dx^2 U0/2, dB = -dx U1,
 // dC = -U2/2, do = U0/o.   "Colour behind" is tracked as R <- R + alpha (c - R) (no delayed update).
-constexpr int kBwdThreads = 32;                 // ONE independent warp per CTA: no block barriers at all
+//
+// SEGMENTS.  A long list no longer serialises on one warp: the forward checkpoints (T, C, D) per pixel at every
+// 256-record boundary it crosses (binning buffer `ckpt`, slot = list position >> 8), so the replay of segment
+// [s0, s1) can start from   T = T_ckpt(s1),  R = (C_final - C_ckpt(s1)) / T_ckpt(s1)   for every pixel whose last
+// contributor lies beyond s1 (and from T_final, R = 0 for the pixels that end inside it) -- exactly the state the
+// sequential back-to-front walk has when it reaches s1.  Work units = 2 per tile (first segment of every tile) + 2 per
+// checkpoint slot; PERSISTENT warps (4 independent warps per CTA, own shared-memory stages and mbarriers, no block
+// barrier) fetch units from a global counter, so long and short lists balance across the 148 SMs.
+constexpr int kBwdWarps = 4;
+constexpr int kBwdThreads = 32 * kBwdWarps;
 constexpr int kBwdBatch = 64;
 constexpr int kPix = 4;
+constexpr int kSeg = 256;                       // == kBatch: the forward checkpoints once per staged batch
 
-__global__ void __launch_bounds__(kBwdThreads)
+__global__ void __launch_bounds__(kBwdThreads, 4)
 k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ recs, int W, int H, int Tx,
              int row0, const float* __restrict__ bg, int normalize, float alpha_max, const float* __restrict__ final_T,
              const uint32_t* __restrict__ n_contrib, const float* __restrict__ depth_raw,
+             const float* __restrict__ color_acc, const float* __restrict__ ckpt,
+             const uint32_t* __restrict__ slot_tile, uint32_t* __restrict__ work_counter, int n_first, int n_units,
              const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
              const float* __restrict__ dL_dalpha, const float* __restrict__ t_target,
              const float* __restrict__ t_weight, const float* __restrict__ t_scale,
              const float* __restrict__ t_gscale, int t_mode,
              int t_row0, int t_row1, float* __restrict__ residual, float* __restrict__ sgrad) {
-    __shared__ __align__(128) float4 sbuf[2][kBwdBatch * 3];
-    __shared__ __align__(8) uint64_t full[2];
-    const int lane = threadIdx.x;
-    const int half = blockIdx.x & 1;                 // upper / lower 16x8 half of the tile
-    const int tile = (blockIdx.x >> 1) + row0 * Tx;
-    const uint2 rng = ranges[tile];
-    const int len = (int)(rng.y - rng.x);
-    const int tx = tile % Tx, ty = tile / Tx;
-    const int px = tx * TGS_TILE + (lane & 15);
-    const int py0 = ty * TGS_TILE + half * 8 + (lane >> 4) * kPix;
-    PixelMap pm;                                   // only the cull rectangle of this warp is used
-    pm.x0 = (float)(tx * TGS_TILE); pm.x1 = pm.x0 + 15.0f;
-    pm.y0 = (float)(ty * TGS_TILE + half * 8); pm.y1 = pm.y0 + 7.0f;
-    const float fx = (float)px, fy0 = (float)py0;
-
-    // ---- per-pixel state and the FUSED touch-depth gradient (SURVEY A6 "Fusion")
-    float T[kPix], g0[kPix], g1[kPix], g2[kPix], gD[kPix], tail[kPix];
-    uint32_t nc[kPix];
-    uint32_t wmax = 0;
+    __shared__ __align__(128) float4 sbuf_all[kBwdWarps][2][kBwdBatch * 3];
+    __shared__ __align__(8) uint64_t full_all[kBwdWarps][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4 (*sbuf)[kBwdBatch * 3] = sbuf_all[warp];
+    uint64_t* full = full_all[warp];
+    if (lane == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
+    __syncwarp();
+    uint32_t phase0 = 0, phase1 = 0;               // completed phases of the warp's two stage barriers
     const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
     // loss scale (mult / Z) times the upstream gradient of the touch-loss scalar (NULL = 1: the loss enters the
     // caller's objective with unit weight)
     const float tscale = (t_target != nullptr && t_mode != TGS_LOSS_NONE)
                              ? t_scale[0] * (t_gscale ? t_gscale[0] : 1.0f) : 0.0f;
+    const size_t HW = (size_t)W * H;
+
+    for (;;) {
+        uint32_t u = 0;
+        if (lane == 0) u = atomicAdd(work_counter, 1u);
+        u = __shfl_sync(kFull, u, 0);
+        if (u >= (uint32_t)n_units) break;
+        // ---- decode the work unit: (tile, half, segment)
+        int tile, half, seg;
+        uint2 rng;
+        if (u < (uint32_t)n_first) {
+            tile = (int)(u >> 1) + row0 * Tx; half = (int)(u & 1u); seg = 0;
+            rng = ranges[tile];
+        } else {
+            const uint32_t slot = (u - (uint32_t)n_first) >> 1;
+            half = (int)((u - (uint32_t)n_first) & 1u);
+            const uint32_t t = slot_tile[slot];
+            if (t == TGS_NO_TILE) continue;            // the forward never crossed a boundary in this slot
+            tile = (int)t;
+            rng = ranges[tile];
+            seg = (int)(slot - (rng.x >> 8));
+        }
+        const int len = (int)(rng.y - rng.x);
+        const int s0 = seg * kSeg;                     // this unit replays list positions [s0, s1)
+        const int s1 = min(len, s0 + kSeg);
+        const int tx = tile % Tx, ty = tile / Tx;
+        const int px = tx * TGS_TILE + (lane & 15);
+        const int py0 = ty * TGS_TILE + half * 8 + (lane >> 4) * kPix;
+        PixelMap pm;                                   // only the cull rectangle of this warp is used
+        pm.x0 = (float)(tx * TGS_TILE); pm.x1 = pm.x0 + 15.0f;
+        pm.y0 = (float)(ty * TGS_TILE + half * 8); pm.y1 = pm.y0 + 7.0f;
+        const float fx = (float)px, fy0 = (float)py0;
+
+        // ---- per-pixel state and the FUSED touch-depth gradient (SURVEY A6 "Fusion")
+        float T[kPix], g0[kPix], g1[kPix], g2[kPix], gD[kPix], tail[kPix];
+        float R0[kPix], R1[kPix], R2[kPix], RD[kPix];   // colour / depth composited BEHIND the current splat
+        uint32_t nc[kPix];
+        uint32_t wmax = 0;
+        const float* ck = ckpt + (size_t)((rng.x + (uint32_t)s1) >> 8) * TGS_CKPT_FLOATS;
 #pragma unroll
-    for (int r = 0; r < kPix; ++r) {
-        const int py = py0 + r;
-        T[r] = 1.0f; g0[r] = g1[r] = g2[r] = gD[r] = tail[r] = 0.0f; nc[r] = 0;
-        if (px < W && py < H) {
-            const int pix = py * W + px;
-            const size_t HW = (size_t)W * H;
-            const float Tf = final_T[pix];
-            T[r] = Tf;
-            nc[r] = n_contrib[pix];
-            g0[r] = dL_dcolor[pix]; g1[r] = dL_dcolor[HW + pix]; g2[r] = dL_dcolor[2 * HW + pix];
-            const float A = 1.0f - Tf;
-            const float D = depth_raw[pix];
-            float gDhat = dL_ddepth ? dL_ddepth[pix] : 0.0f;
-            float gA = dL_dalpha ? dL_dalpha[pix] : 0.0f;
-            float res = 0.0f;
-            if (t_target != nullptr && A > 0.0f && py >= t_row0 && py < t_row1) {
-                const float tgt = t_target[pix];
-                if (tgt > 0.0f) {
-                    const float dhat = normalize ? D / A : D;
-                    res = dhat - tgt;
-                    if (t_mode != TGS_LOSS_NONE) {
-                        const float wgt = (t_weight ? t_weight[pix] : 1.0f) * tscale;
-                        gDhat += (t_mode == TGS_LOSS_L1) ? wgt * (float)((res > 0.0f) - (res < 0.0f))
-                                                         : 2.0f * wgt * res;
+        for (int r = 0; r < kPix; ++r) {
+            const int py = py0 + r;
+            T[r] = 1.0f; g0[r] = g1[r] = g2[r] = gD[r] = tail[r] = 0.0f; nc[r] = 0;
+            R0[r] = R1[r] = R2[r] = RD[r] = 0.0f;
+            if (px < W && py < H) {
+                const int pix = py * W + px;
+                const uint32_t ncp = n_contrib[pix];
+                const float Tf = final_T[pix];
+                const float A = 1.0f - Tf;
+                const float D = depth_raw[pix];
+                float res = 0.0f;
+                float gDhat = dL_ddepth ? dL_ddepth[pix] : 0.0f;
+                const bool touch_px = t_target != nullptr && A > 0.0f && py >= t_row0 && py < t_row1;
+                if (ncp > (uint32_t)s0 || (seg == 0 && residual != nullptr)) {
+                    if (touch_px) {
+                        const float tgt = t_target[pix];
+                        if (tgt > 0.0f) {
+                            const float dhat = normalize ? D / A : D;
+                            res = dhat - tgt;
+                            if (t_mode != TGS_LOSS_NONE) {
+                                const float wgt = (t_weight ? t_weight[pix] : 1.0f) * tscale;
+                                gDhat += (t_mode == TGS_LOSS_L1) ? wgt * (float)((res > 0.0f) - (res < 0.0f))
+                                                                 : 2.0f * wgt * res;
+                            }
+                        }
                     }
+                    if (seg == 0 && residual) residual[pix] = res;
                 }
-            }
-            if (residual) residual[pix] = res;
-            if (normalize) {
-                if (A > 0.0f) { gD[r] = gDhat / A; gA -= gDhat * D / (A * A); }
-            } else {
-                gD[r] = gDhat;
-            }
-            // colour: d(T_final*bg)/dalpha_i = -T_final/(1-alpha_i)*bg ; alpha: dA/dalpha_i = +T_final/(1-alpha_i)
-            tail[r] = Tf * (gA - (bg0 * g0[r] + bg1 * g1[r] + bg2 * g2[r]));
-            wmax = max(wmax, nc[r]);
-        }
-    }
-    // ---- nothing beyond the deepest contributor of any pixel of this half tile needs replaying
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(kFull, wmax, o));
-    const int leff = min(len, (int)wmax);
-    const int nb = (leff + kBwdBatch - 1) / kBwdBatch;
-    if (nb == 0) return;
-    if (lane == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
-    __syncwarp();
-
-    const TgsRecord* src = recs + rng.x;
-    auto issue = [&](int q) {                       // sequence step q stages batch nb-1-q (back to front)
-        int b = nb - 1 - q;
-        int cnt = min(kBwdBatch, leff - b * kBwdBatch);
-        uint32_t bytes = (uint32_t)cnt * kRecBytes;
-        mbar_expect_tx(&full[q & 1], bytes);
-        tma_bulk_g2s(sbuf[q & 1], src + (size_t)b * kBwdBatch, bytes, &full[q & 1]);
-    };
-    if (lane == 0) { issue(0); if (nb > 1) issue(1); }
-
-    float R0[kPix], R1[kPix], R2[kPix], RD[kPix];   // colour / depth composited BEHIND the current splat
-#pragma unroll
-    for (int r = 0; r < kPix; ++r) R0[r] = R1[r] = R2[r] = RD[r] = 0.0f;
-
-    for (int q = 0; q < nb; ++q) {
-        mbar_wait(&full[q & 1], (uint32_t)((q >> 1) & 1));
-        const int b = nb - 1 - q;
-        const int cnt = min(kBwdBatch, leff - b * kBwdBatch);
-        const float4* s = sbuf[q & 1];
-        const int base = b * kBwdBatch;
-        for (int c0 = ((cnt - 1) >> 5) << 5; c0 >= 0; c0 -= 32) {
-            const int jl = c0 + lane;
-            bool pass = false;
-            if (jl < cnt) pass = patch_may_touch(s[3 * jl], s[3 * jl + 1], s[3 * jl + 2].w, pm);
-            unsigned mask = __ballot_sync(kFull, pass);
-            while (mask) {
-                const int hb = 31 - __clz(mask);
-                mask &= ~(1u << hb);
-                const int j = c0 + hb;
-                const uint32_t idx = (uint32_t)(base + j);
-                const float4 a = s[3 * j], cq = s[3 * j + 1];
-                // same pinned rounding sequence as splat_power(): ax, ax*dx and B*dx are shared by the 4 pixels
-                const float dx = a.x - fx;
-                const float t1 = __fmul_rn(__fmul_rn(cq.x, dx), dx);
-                const float bxd = __fmul_rn(cq.y, dx);
-                float og[kPix], dy[kPix];             // og = o*G where the pixel blends this splat, else 0
-                bool anyv = false;
-#pragma unroll
-                for (int r = 0; r < kPix; ++r) {
-                    dy[r] = a.y - (fy0 + (float)r);
-                    const float sq = __fmaf_rn(__fmul_rn(cq.z, dy[r]), dy[r], t1);
-                    const float power = __fmaf_rn(-0.5f, sq, -__fmul_rn(bxd, dy[r]));
-                    const float oG = __fmul_rn(cq.w, splat_exp(power));
-                    const bool valid = (idx < nc[r]) && (power <= 0.0f) && (oG >= TGS_ALPHA_MIN);   // min(0.99,oG) >= 1/255 <=> oG >= 1/255
-                    og[r] = valid ? oG : 0.0f;
-                    anyv |= valid;
+                if (ncp > (uint32_t)s0) {              // this pixel blends something inside [s0, s1)
+                    nc[r] = ncp;
+                    g0[r] = dL_dcolor[pix]; g1[r] = dL_dcolor[HW + pix]; g2[r] = dL_dcolor[2 * HW + pix];
+                    float gA = dL_dalpha ? dL_dalpha[pix] : 0.0f;
+                    if (normalize) {
+                        if (A > 0.0f) { gD[r] = gDhat / A; gA -= gDhat * D / (A * A); }
+                    } else {
+                        gD[r] = gDhat;
+                    }
+                    // colour: d(T_final*bg)/dalpha_i = -T_final/(1-alpha_i)*bg ; alpha: dA/dalpha_i = +T_final/(1-alpha_i)
+                    tail[r] = Tf * (gA - (bg0 * g0[r] + bg1 * g1[r] + bg2 * g2[r]));
+                    if (ncp <= (uint32_t)s1) {
+                        T[r] = Tf;                     // the pixel's last contributor lies in this segment
+                    } else {
+                        // state of the sequential walk when it arrives at s1, from the forward's checkpoint
+                        const int pidx = ((py & 15) << 4) + (px & 15);
+                        const float Tc = ck[pidx];
+                        const float iT = 1.0f / Tc;      // Tc >= 1e-4: the pixel was still alive at s1
+                        T[r] = Tc;
+                        R0[r] = (color_acc[pix] - ck[256 + pidx]) * iT;
+                        R1[r] = (color_acc[HW + pix] - ck[512 + pidx]) * iT;
+                        R2[r] = (color_acc[2 * HW + pix] - ck[768 + pidx]) * iT;
+                        RD[r] = (D - ck[1024 + pidx]) * iT;
+                    }
+                    wmax = max(wmax, min(ncp, (uint32_t)s1));
                 }
-                if (!__any_sync(kFull, anyv)) continue;
-                const float4 c = s[3 * j + 2];
-                float U0 = 0.f, U1 = 0.f, U2 = 0.f, V0 = 0.f, V1 = 0.f, V2 = 0.f, VD = 0.f;
-#pragma unroll
-                for (int r = 0; r < kPix; ++r) {
-                    // pixels that do not blend this splat run with og == 0: alpha == 0, inv == 1, T untouched,
-                    // u == 0 and w == 0, so every gradient term is exactly 0 without any branch
-                    const float am = fminf(alpha_max, og[r]);
-                    const float inv = fast_rcp(1.0f - am);
-                    T[r] *= inv;                               // transmittance in front of this splat
-                    const float w = am * T[r];
-                    const float d0 = c.x - R0[r], d1 = c.y - R1[r], d2 = c.z - R2[r], dD = a.z - RD[r];
-                    float dLda = d0 * g0[r] + d1 * g1[r] + d2 * g2[r] + dD * gD[r];
-                    dLda = fmaf(dLda, T[r], tail[r] * inv);
-                    R0[r] = fmaf(am, d0, R0[r]); R1[r] = fmaf(am, d1, R1[r]);
-                    R2[r] = fmaf(am, d2, R2[r]); RD[r] = fmaf(am, dD, RD[r]);
-                    const float u = og[r] * dLda;              // straight-through alpha clamp: o*G, not alpha
-                    U0 += u;
-                    const float udy = u * dy[r];
-                    U1 += udy;
-                    U2 = fmaf(udy, dy[r], U2);
-                    V0 = fmaf(w, g0[r], V0); V1 = fmaf(w, g1[r], V1); V2 = fmaf(w, g2[r], V2);
-                    VD = fmaf(w, gD[r], VD);
-                }
-                float v[TGS_NGRAD];
-                const float dxU0 = dx * U0;
-                v[0] = -(cq.x * dxU0 + cq.y * U1);
-                v[1] = -(cq.z * U1 + cq.y * dxU0);
-                v[2] = -0.5f * dx * dxU0;
-                v[3] = -dx * U1;
-                v[4] = -0.5f * U2;
-                v[5] = U0 * fast_rcp(cq.w);
-                v[6] = V0; v[7] = V1; v[8] = V2; v[9] = VD;
-                float sum; int slot; bool ok;
-                warp_reduce_scatter10(v, lane, sum, slot, ok);
-                if (ok) atomicAdd(sgrad + (size_t)__float_as_int(a.w) * TGS_NGRAD + slot, sum);
             }
         }
-        __syncwarp();
-        if (lane == 0 && q + 2 < nb) issue(q + 2);
+        // ---- nothing beyond the deepest contributor of any pixel of this half tile needs replaying
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(kFull, wmax, o));
+        const int leff = (int)wmax - s0;               // records of the segment to replay (<= 0: none)
+        const int nb = (leff + kBwdBatch - 1) / kBwdBatch;
+        if (nb <= 0) continue;
+
+        const TgsRecord* src = recs + rng.x + s0;
+        auto issue = [&](int q) {                       // sequence step q stages batch nb-1-q (back to front)
+            int b = nb - 1 - q;
+            int cnt = min(kBwdBatch, leff - b * kBwdBatch);
+            uint32_t bytes = (uint32_t)cnt * kRecBytes;
+            mbar_expect_tx(&full[q & 1], bytes);
+            tma_bulk_g2s(sbuf[q & 1], src + (size_t)b * kBwdBatch, bytes, &full[q & 1]);
+        };
+        if (lane == 0) { issue(0); if (nb > 1) issue(1); }
+
+        for (int q = 0; q < nb; ++q) {
+            if (q & 1) { mbar_wait(&full[1], phase1 & 1u); ++phase1; }
+            else       { mbar_wait(&full[0], phase0 & 1u); ++phase0; }
+            const int b = nb - 1 - q;
+            const int cnt = min(kBwdBatch, leff - b * kBwdBatch);
+            const float4* s = sbuf[q & 1];
+            const int base = s0 + b * kBwdBatch;
+            for (int c0 = ((cnt - 1) >> 5) << 5; c0 >= 0; c0 -= 32) {
+                const int jl = c0 + lane;
+                bool pass = false;
+                if (jl < cnt) pass = patch_may_touch(s[3 * jl], s[3 * jl + 1], s[3 * jl + 2].w, pm);
+                unsigned mask = __ballot_sync(kFull, pass);
+                while (mask) {
+                    const int hb = 31 - __clz(mask);
+                    mask &= ~(1u << hb);
+                    const int j = c0 + hb;
+                    const uint32_t idx = (uint32_t)(base + j);
+                    const float4 a = s[3 * j], cq = s[3 * j + 1];
+                    // same pinned rounding sequence as splat_power(): ax, ax*dx and B*dx are shared by the 4 pixels
+                    const float dx = a.x - fx;
+                    const float t1 = __fmul_rn(__fmul_rn(cq.x, dx), dx);
+                    const float bxd = __fmul_rn(cq.y, dx);
+                    float og[kPix], dy[kPix];             // og = o*G where the pixel blends this splat, else 0
+                    bool anyv = false;
+#pragma unroll
+                    for (int r = 0; r < kPix; ++r) {
+                        dy[r] = a.y - (fy0 + (float)r);
+                        const float sq = __fmaf_rn(__fmul_rn(cq.z, dy[r]), dy[r], t1);
+                        const float power = __fmaf_rn(-0.5f, sq, -__fmul_rn(bxd, dy[r]));
+                        const float oG = __fmul_rn(cq.w, splat_exp(power));
+                        const bool valid = (idx < nc[r]) && (power <= 0.0f) && (oG >= TGS_ALPHA_MIN);   // min(0.99,oG) >= 1/255 <=> oG >= 1/255
+                        og[r] = valid ? oG : 0.0f;
+                        anyv |= valid;
+                    }
+                    if (!__any_sync(kFull, anyv)) continue;
+                    const float4 c = s[3 * j + 2];
+                    float U0 = 0.f, U1 = 0.f, U2 = 0.f, V0 = 0.f, V1 = 0.f, V2 = 0.f, VD = 0.f;
+#pragma unroll
+                    for (int r = 0; r < kPix; ++r) {
+                        // pixels that do not blend this splat run with og == 0: alpha == 0, inv == 1, T untouched,
+                        // u == 0 and w == 0, so every gradient term is exactly 0 without any branch
+                        const float am = fminf(alpha_max, og[r]);
+                        const float inv = fast_rcp(1.0f - am);
+                        T[r] *= inv;                               // transmittance in front of this splat
+                        const float w = am * T[r];
+                        const float d0 = c.x - R0[r], d1 = c.y - R1[r], d2 = c.z - R2[r], dD = a.z - RD[r];
+                        float dLda = d0 * g0[r] + d1 * g1[r] + d2 * g2[r] + dD * gD[r];
+                        dLda = fmaf(dLda, T[r], tail[r] * inv);
+                        R0[r] = fmaf(am, d0, R0[r]); R1[r] = fmaf(am, d1, R1[r]);
+                        R2[r] = fmaf(am, d2, R2[r]); RD[r] = fmaf(am, dD, RD[r]);
+                        const float uu = og[r] * dLda;             // straight-through alpha clamp: o*G, not alpha
+                        U0 += uu;
+                        const float udy = uu * dy[r];
+                        U1 += udy;
+                        U2 = fmaf(udy, dy[r], U2);
+                        V0 = fmaf(w, g0[r], V0); V1 = fmaf(w, g1[r], V1); V2 = fmaf(w, g2[r], V2);
+                        VD = fmaf(w, gD[r], VD);
+                    }
+                    float v[TGS_NGRAD];
+                    const float dxU0 = dx * U0;
+                    v[0] = -(cq.x * dxU0 + cq.y * U1);
+                    v[1] = -(cq.z * U1 + cq.y * dxU0);
+                    v[2] = -0.5f * dx * dxU0;
+                    v[3] = -dx * U1;
+                    v[4] = -0.5f * U2;
+                    v[5] = U0 * fast_rcp(cq.w);
+                    v[6] = V0; v[7] = V1; v[8] = V2; v[9] = VD;
+                    float sum; int slot; bool ok;
+                    warp_reduce_scatter10(v, lane, sum, slot, ok);
+                    if (ok) atomicAdd(sgrad + (size_t)__float_as_int(a.w) * TGS_NGRAD + slot, sum);
+                }
+            }
+            __syncwarp();
+            if (lane == 0 && q + 2 < nb) issue(q + 2);
+        }
     }
 }
 
@@ -481,13 +545,14 @@ int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, BinView bv, I
     TgsProfScope prof(TGS_STAGE_RENDER_FWD, st);
     k_render_fwd<<<nt, 256, 0, st>>>(bv.ranges, bv.records, cam.W, cam.H, cam.Tx, cam.row0, s->bg,
                                      s->depth_normalize, cam.alpha_max, out_color, out_depth, out_alpha, iv.final_T,
-                                     iv.n_contrib, iv.depth_raw, touch_target, residual_out);
+                                     iv.n_contrib, iv.depth_raw, iv.color_acc, bv.ckpt, bv.slot_tile, touch_target,
+                                     residual_out);
     tgs_count_own(1);
     TGS_KERNEL_CHECK(st, s->debug);
     return 0;
 }
 
-int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, BinView bv, ImageView iv,
+int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, BinView bv, ImageView iv, int64_t num_rendered,
                           const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
                           const TgsTouch* touch, float* residual, float* screen_grads, cudaStream_t st) {
     int nt = cam.Tx * (cam.row1 - cam.row0);
@@ -501,8 +566,26 @@ int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, BinView bv, I
         if (mode != TGS_LOSS_NONE && ts == nullptr) { tgs_set_error("touch loss enabled but scale pointer is NULL"); return TGS_EINVAL; }
     }
     TgsProfScope prof(TGS_STAGE_RENDER_BWD, st);
-    k_render_bwd<<<2 * nt, kBwdThreads, 0, st>>>(bv.ranges, bv.records, cam.W, cam.H, cam.Tx, cam.row0, s->bg,
-                                     s->depth_normalize, cam.alpha_max, iv.final_T, iv.n_contrib, iv.depth_raw, dL_dcolor,
+    // work units: two half tiles per tile (first segment) + two per 256-record checkpoint slot of the sorted list
+    const int64_t slots = (num_rendered + 255) >> 8;
+    const int64_t units = 2 * (int64_t)nt + 2 * slots;
+    if (units > 0x7FFFFFFFll) { tgs_set_error("render backward: too many work units"); return TGS_EINVAL; }
+    static int ctas_per_sm[64] = {};
+    static int sm_count[64] = {};
+    int dev = 0;
+    TGS_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && ctas_per_sm[dev] == 0) {
+        TGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[dev], k_render_bwd, kBwdThreads, 0));
+        TGS_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int cps = (dev >= 0 && dev < 64 && ctas_per_sm[dev] > 0) ? ctas_per_sm[dev] : 4;
+    const int sms = (dev >= 0 && dev < 64 && sm_count[dev] > 0) ? sm_count[dev] : 148;
+    int64_t grid = (units + kBwdWarps - 1) / kBwdWarps;
+    if (grid > (int64_t)cps * sms) grid = (int64_t)cps * sms;        // persistent: one resident wave
+    TGS_CUDA(cudaMemsetAsync(bv.work_counter, 0, sizeof(uint32_t), st));
+    k_render_bwd<<<(unsigned)grid, kBwdThreads, 0, st>>>(bv.ranges, bv.records, cam.W, cam.H, cam.Tx, cam.row0, s->bg,
+                                     s->depth_normalize, cam.alpha_max, iv.final_T, iv.n_contrib, iv.depth_raw,
+                                     iv.color_acc, bv.ckpt, bv.slot_tile, bv.work_counter, 2 * nt, (int)units, dL_dcolor,
                                      dL_ddepth, dL_dalpha, tt, tw, ts, tg, mode, tr0, tr1, residual, screen_grads);
     tgs_count_own(1);
     TGS_KERNEL_CHECK(st, s->debug);

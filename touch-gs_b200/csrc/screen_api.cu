@@ -189,7 +189,8 @@ extern "C" int tgs_rasterize_screen_backward(const TgsSettings* s, int32_t N, co
     if (N > 0) TGS_CUDA(cudaMemsetAsync(screen_grads, 0, sizeof(float) * TGS_NGRAD * (size_t)N, st));
     TgsSettings s2 = *s;
     s2.depth_normalize = 0;
-    return tgs_launch_render_bwd(cam, &s2, bv, iv, dL_dcolor, dL_ddepth, dL_dalpha, nullptr, nullptr, screen_grads, st);
+    return tgs_launch_render_bwd(cam, &s2, bv, iv, saved->num_rendered, dL_dcolor, dL_ddepth, dL_dalpha, nullptr, nullptr,
+                                 screen_grads, st);
 }
 
 extern "C" int tgs_spherical_harmonics(int32_t N, int32_t degree, int32_t K, const float* dirs, const float* coeffs,

@@ -66,9 +66,15 @@ struct BinView {
     uint2* ranges;           // [T]
     TgsRecord* records;      // [I] packed, sorted
     void* cub_temp; size_t cub_temp_bytes;
+    float* ckpt;             // [slots][5][256] forward checkpoints at 256-record boundaries of the tile lists
+    uint32_t* slot_tile;     // [slots] owning tile of the boundary in a slot, TGS_NO_TILE = none
+    uint32_t* work_counter;  // dynamic work-unit counter of the backward
 };
+#define TGS_CKPT_FLOATS (5 * 256)
+#define TGS_NO_TILE 0xFFFFFFFFu
 struct ImageView {
     float* final_T; uint32_t* n_contrib; float* depth_raw;
+    float* color_acc;        // [3][H*W] composited colour without the background term
 };
 GeomView tgs_geom_view(void* base, int N);
 BinView tgs_bin_view(void* base, int64_t I, int T);
@@ -96,7 +102,7 @@ int tgs_emit_sort_pack(GeomView gv, BinView bv, int N, int64_t count, int64_t ca
 int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, BinView bv, ImageView iv,
                           float* out_color, float* out_depth, float* out_alpha,
                           const float* touch_target, float* residual_out, cudaStream_t st);
-int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, BinView bv, ImageView iv,
+int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, BinView bv, ImageView iv, int64_t num_rendered,
                           const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
                           const TgsTouch* touch, float* residual, float* screen_grads, cudaStream_t st);
 int tgs_launch_loss_scale(const float* target, int64_t P, float mult, float norm, float* out, cudaStream_t st);
