@@ -291,8 +291,9 @@ typedef struct TgsBinningLayout {
                                * ranges[tile].x + 256k, written by the forward for every 256-record boundary it crosses;
                                * slot = that position >> 8 (unique per boundary).  Lets the backward replay a tile's list
                                * in independent 256-record segments. */
-    size_t slot_tile;         /* uint32[slots]: tile that owns the boundary in this slot, 0xFFFFFFFF = none */
-    size_t work_counter;      /* uint32: dynamic work-unit counter of the backward */
+    size_t slot_tile;         /* uint32[slots]: tile that owns the boundary in this slot (valid for listed slots) */
+    size_t ckpt_list;         /* uint32[slots]: the slots the forward wrote, in completion order */
+    size_t work_counter;      /* uint32[2]: [0] dynamic work-unit counter of the backward, [1] length of ckpt_list */
     size_t slots;             /* (I >> 8) + 2 */
     size_t total;
 } TgsBinningLayout;

@@ -67,7 +67,7 @@ class TgsGeomLayout(C.Structure):
 class TgsBinningLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in
                 ("ranges", "records", "tile_sorted", "vals_sorted", "tile_unsorted", "vals_unsorted",
-                 "sort_temp", "sort_temp_bytes", "key_bytes", "ckpt", "slot_tile", "work_counter", "slots", "total")]
+                 "sort_temp", "sort_temp_bytes", "key_bytes", "ckpt", "slot_tile", "ckpt_list", "work_counter", "slots", "total")]
 
 
 class TgsImageLayout(C.Structure):

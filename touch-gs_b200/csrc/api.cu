@@ -111,7 +111,8 @@ extern "C" int tgs_binning_layout(int64_t I, int32_t T, TgsBinningLayout* o) {
     o->slots = (n >> 8) + 2;
     o->ckpt = c.take(o->slots * TGS_CKPT_FLOATS * sizeof(float));
     o->slot_tile = c.take(o->slots * sizeof(uint32_t));
-    o->work_counter = c.take(sizeof(uint32_t));
+    o->ckpt_list = c.take(o->slots * sizeof(uint32_t));
+    o->work_counter = c.take(2 * sizeof(uint32_t));
     o->total = c.off;
     return 0;
 }
@@ -144,6 +145,7 @@ BinView tgs_bin_view(void* base, int64_t I, int T) {
     v.tile_unsorted = b + l.tile_unsorted; v.vals_unsorted = (uint32_t*)(b + l.vals_unsorted);
     v.cub_temp = b + l.sort_temp; v.cub_temp_bytes = l.sort_temp_bytes;
     v.ckpt = (float*)(b + l.ckpt); v.slot_tile = (uint32_t*)(b + l.slot_tile);
+    v.ckpt_list = (uint32_t*)(b + l.ckpt_list);
     v.work_counter = (uint32_t*)(b + l.work_counter);
     return v;
 }

@@ -86,10 +86,8 @@ template <typename KeyT>
 __global__ void __launch_bounds__(256)
 k_pack_ranges(int64_t I_host, const uint32_t* __restrict__ I_dev, int64_t cap, const KeyT* __restrict__ keys,
               const uint32_t* __restrict__ vals, const float4* __restrict__ rec_in, float4* __restrict__ rec_out,
-              uint2* __restrict__ ranges, uint32_t* __restrict__ slot_tile) {
+              uint2* __restrict__ ranges) {
     __shared__ __align__(128) float4 sm[256 * 3];
-    // checkpoint slot of the 256-record block this CTA packs: no owner until the forward crosses a boundary in it
-    if (threadIdx.x == 0) slot_tile[blockIdx.x] = TGS_NO_TILE;
     // exact mode: I_host; speculative mode: the real count lives on the device (last scan element), clamped
     // to the buffer capacity (an overflowing speculation is discarded and re-run by the host)
     int64_t I = I_host;
@@ -150,7 +148,7 @@ int emit_sort_pack(GeomView gv, BinView bv, int N, int64_t I, int64_t cap, bool 
         TgsProfScope prof(TGS_STAGE_PACK, st);
         k_pack_ranges<KeyT><<<(unsigned)((I + 255) / 256), 256, 0, st>>>(
             I, spec ? gv.offsets + (N - 1) : nullptr, cap, ks, bv.vals_sorted,
-            reinterpret_cast<const float4*>(gv.records), reinterpret_cast<float4*>(bv.records), bv.ranges, bv.slot_tile);
+            reinterpret_cast<const float4*>(gv.records), reinterpret_cast<float4*>(bv.records), bv.ranges);
         tgs_count_own(1);
         TGS_CUDA(cudaGetLastError());
     }

@@ -131,7 +131,8 @@ k_render_fwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
              int row0, const float* __restrict__ bg, int normalize, float alpha_max, float* __restrict__ out_color,
              float* __restrict__ out_depth, float* __restrict__ out_alpha, float* __restrict__ final_T,
              uint32_t* __restrict__ n_contrib, float* __restrict__ depth_raw, float* __restrict__ color_acc,
-             float* __restrict__ ckpt, uint32_t* __restrict__ slot_tile,
+             float* __restrict__ ckpt, uint32_t* __restrict__ slot_tile, uint32_t* __restrict__ ckpt_list,
+             uint32_t* __restrict__ ckpt_count,
              const float* __restrict__ t_target, float* __restrict__ residual) {
     __shared__ __align__(128) float4 sbuf[2][kBatch * 3];
     __shared__ __align__(8) uint64_t full[2];
@@ -195,7 +196,7 @@ k_render_fwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
             const uint32_t slot = (rng.x + (uint32_t)(b + 1) * kBatch) >> 8;   // unique per (tile, boundary)
             float* ck = ckpt + (size_t)slot * TGS_CKPT_FLOATS + ((pm.py & 15) * 16 + (pm.px & 15));
             ck[0] = T; ck[256] = C0; ck[512] = C1; ck[768] = C2; ck[1024] = D;
-            if (tid == 0) slot_tile[slot] = (uint32_t)tile;
+            if (tid == 0) { slot_tile[slot] = (uint32_t)tile; ckpt_list[atomicAdd(ckpt_count, 1u)] = slot; }
         }
     }
     // a copy issued for batch b+1 may still be in flight if we broke out early: the CTA must not
@@ -207,7 +208,9 @@ k_render_fwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
         out_color[pm.pix] = C0 + T * bg[0];
         out_color[HW + pm.pix] = C1 + T * bg[1];
         out_color[2 * HW + pm.pix] = C2 + T * bg[2];
-        color_acc[pm.pix] = C0; color_acc[HW + pm.pix] = C1; color_acc[2 * HW + pm.pix] = C2;
+        if (last > (uint32_t)kBatch) {      // only pixels that blend beyond the first segment are re-based in backward
+            color_acc[pm.pix] = C0; color_acc[HW + pm.pix] = C1; color_acc[2 * HW + pm.pix] = C2;
+        }
         const float A = 1.0f - T;
         out_alpha[pm.pix] = A;
         const float dhat = normalize ? (A > 0.0f ? D / A : 0.0f) : D;
@@ -257,12 +260,15 @@ __device__ __forceinline__ void warp_reduce_scatter10(const float (&v)[TGS_NGRAD
 // dL/dopacity collapse into three per-thread moments
 //   U0 = sum u,  U1 = sum u*dy,  U2 = sum u*dy^2     with u = o*G*dL/dalpha
 // from which  d/dx = -(A dx U0 + B U1), d/dy = -(C U1 + B dx U0), dA = -dx^2 U0/2, dB = -dx U1,
-// dC = -U2/2, do = U0/o.   "Colour behind" is tracked as R <- R + alpha (c - R) (no delayed update).
+// dC = -U2/2, do = U0/o.   The colour / depth composited BEHIND a splat enters dL/dalpha only through its dot product
+// with the pixel's gradient vector g = (g_r, g_g, g_b, g_D), so it is tracked as ONE scalar per pixel:
+//   h_i = c_i . g,   dL/dalpha_i = h_i T_i + Q_i / (1 - alpha_i),   Q_i = tail - sum_{j>i} h_j alpha_j T_j
+// (tail = T_final (g_A - bg . g): the background and alpha-channel terms), updated as Q <- Q - h_i w_i.
 //
 // SEGMENTS.  A long list no longer serialises on one warp: the forward checkpoints (T, C, D) per pixel at every
 // 256-record boundary it crosses (binning buffer `ckpt`, slot = list position >> 8), so the replay of segment
-// [s0, s1) can start from   T = T_ckpt(s1),  R = (C_final - C_ckpt(s1)) / T_ckpt(s1)   for every pixel whose last
-// contributor lies beyond s1 (and from T_final, R = 0 for the pixels that end inside it) -- exactly the state the
+// [s0, s1) can start from   T = T_ckpt(s1),  Q = tail - g . (C_final - C_ckpt(s1))   for every pixel whose last
+// contributor lies beyond s1 (and from T_final, Q = tail for the pixels that end inside it) -- exactly the state the
 // sequential back-to-front walk has when it reaches s1.  Work units = 2 per tile (first segment of every tile) + 2 per
 // checkpoint slot; PERSISTENT warps (4 independent warps per CTA, own shared-memory stages and mbarriers, no block
 // barrier) fetch units from a global counter, so long and short lists balance across the 148 SMs.
@@ -272,12 +278,13 @@ constexpr int kBwdBatch = 64;
 constexpr int kPix = 4;
 constexpr int kSeg = 256;                       // == kBatch: the forward checkpoints once per staged batch
 
-__global__ void __launch_bounds__(kBwdThreads, 4)
+__global__ void __launch_bounds__(kBwdThreads, 5)
 k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ recs, int W, int H, int Tx,
              int row0, const float* __restrict__ bg, int normalize, float alpha_max, const float* __restrict__ final_T,
              const uint32_t* __restrict__ n_contrib, const float* __restrict__ depth_raw,
              const float* __restrict__ color_acc, const float* __restrict__ ckpt,
-             const uint32_t* __restrict__ slot_tile, uint32_t* __restrict__ work_counter, int n_first, int n_units,
+             const uint32_t* __restrict__ slot_tile, const uint32_t* __restrict__ ckpt_list,
+             uint32_t* __restrict__ work_counter, int n_first,
              const float* __restrict__ dL_dcolor, const float* __restrict__ dL_ddepth,
              const float* __restrict__ dL_dalpha, const float* __restrict__ t_target,
              const float* __restrict__ t_weight, const float* __restrict__ t_scale,
@@ -297,12 +304,14 @@ k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
     const float tscale = (t_target != nullptr && t_mode != TGS_LOSS_NONE)
                              ? t_scale[0] * (t_gscale ? t_gscale[0] : 1.0f) : 0.0f;
     const size_t HW = (size_t)W * H;
+    // work units: the first segment of both half tiles of every tile, then both halves of every checkpointed slot
+    const uint32_t n_units = (uint32_t)n_first + 2u * work_counter[1];
 
     for (;;) {
         uint32_t u = 0;
         if (lane == 0) u = atomicAdd(work_counter, 1u);
         u = __shfl_sync(kFull, u, 0);
-        if (u >= (uint32_t)n_units) break;
+        if (u >= n_units) break;
         // ---- decode the work unit: (tile, half, segment)
         int tile, half, seg;
         uint2 rng;
@@ -310,11 +319,9 @@ k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
             tile = (int)(u >> 1) + row0 * Tx; half = (int)(u & 1u); seg = 0;
             rng = ranges[tile];
         } else {
-            const uint32_t slot = (u - (uint32_t)n_first) >> 1;
+            const uint32_t slot = ckpt_list[(u - (uint32_t)n_first) >> 1];
             half = (int)((u - (uint32_t)n_first) & 1u);
-            const uint32_t t = slot_tile[slot];
-            if (t == TGS_NO_TILE) continue;            // the forward never crossed a boundary in this slot
-            tile = (int)t;
+            tile = (int)slot_tile[slot];
             rng = ranges[tile];
             seg = (int)(slot - (rng.x >> 8));
         }
@@ -330,16 +337,14 @@ k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
         const float fx = (float)px, fy0 = (float)py0;
 
         // ---- per-pixel state and the FUSED touch-depth gradient (SURVEY A6 "Fusion")
-        float T[kPix], g0[kPix], g1[kPix], g2[kPix], gD[kPix], tail[kPix];
-        float R0[kPix], R1[kPix], R2[kPix], RD[kPix];   // colour / depth composited BEHIND the current splat
+        float T[kPix], g0[kPix], g1[kPix], g2[kPix], gD[kPix], Q[kPix];
         uint32_t nc[kPix];
         uint32_t wmax = 0;
         const float* ck = ckpt + (size_t)((rng.x + (uint32_t)s1) >> 8) * TGS_CKPT_FLOATS;
 #pragma unroll
         for (int r = 0; r < kPix; ++r) {
             const int py = py0 + r;
-            T[r] = 1.0f; g0[r] = g1[r] = g2[r] = gD[r] = tail[r] = 0.0f; nc[r] = 0;
-            R0[r] = R1[r] = R2[r] = RD[r] = 0.0f;
+            T[r] = 1.0f; g0[r] = g1[r] = g2[r] = gD[r] = Q[r] = 0.0f; nc[r] = 0;
             if (px < W && py < H) {
                 const int pix = py * W + px;
                 const uint32_t ncp = n_contrib[pix];
@@ -374,19 +379,18 @@ k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
                         gD[r] = gDhat;
                     }
                     // colour: d(T_final*bg)/dalpha_i = -T_final/(1-alpha_i)*bg ; alpha: dA/dalpha_i = +T_final/(1-alpha_i)
-                    tail[r] = Tf * (gA - (bg0 * g0[r] + bg1 * g1[r] + bg2 * g2[r]));
+                    Q[r] = Tf * (gA - (bg0 * g0[r] + bg1 * g1[r] + bg2 * g2[r]));
                     if (ncp <= (uint32_t)s1) {
                         T[r] = Tf;                     // the pixel's last contributor lies in this segment
                     } else {
                         // state of the sequential walk when it arrives at s1, from the forward's checkpoint
                         const int pidx = ((py & 15) << 4) + (px & 15);
-                        const float Tc = ck[pidx];
-                        const float iT = 1.0f / Tc;      // Tc >= 1e-4: the pixel was still alive at s1
-                        T[r] = Tc;
-                        R0[r] = (color_acc[pix] - ck[256 + pidx]) * iT;
-                        R1[r] = (color_acc[HW + pix] - ck[512 + pidx]) * iT;
-                        R2[r] = (color_acc[2 * HW + pix] - ck[768 + pidx]) * iT;
-                        RD[r] = (D - ck[1024 + pidx]) * iT;
+                        T[r] = ck[pidx];
+                        float behind = g0[r] * (color_acc[pix] - ck[256 + pidx]);
+                        behind = fmaf(g1[r], color_acc[HW + pix] - ck[512 + pidx], behind);
+                        behind = fmaf(g2[r], color_acc[2 * HW + pix] - ck[768 + pidx], behind);
+                        behind = fmaf(gD[r], D - ck[1024 + pidx], behind);
+                        Q[r] -= behind;
                     }
                     wmax = max(wmax, min(ncp, (uint32_t)s1));
                 }
@@ -448,17 +452,15 @@ k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
                     float U0 = 0.f, U1 = 0.f, U2 = 0.f, V0 = 0.f, V1 = 0.f, V2 = 0.f, VD = 0.f;
 #pragma unroll
                     for (int r = 0; r < kPix; ++r) {
-                        // pixels that do not blend this splat run with og == 0: alpha == 0, inv == 1, T untouched,
+                        // pixels that do not blend this splat run with og == 0: alpha == 0, inv == 1, T and Q untouched,
                         // u == 0 and w == 0, so every gradient term is exactly 0 without any branch
+                        const float h = fmaf(a.z, gD[r], fmaf(c.z, g2[r], fmaf(c.y, g1[r], c.x * g0[r])));
                         const float am = fminf(alpha_max, og[r]);
                         const float inv = fast_rcp(1.0f - am);
                         T[r] *= inv;                               // transmittance in front of this splat
                         const float w = am * T[r];
-                        const float d0 = c.x - R0[r], d1 = c.y - R1[r], d2 = c.z - R2[r], dD = a.z - RD[r];
-                        float dLda = d0 * g0[r] + d1 * g1[r] + d2 * g2[r] + dD * gD[r];
-                        dLda = fmaf(dLda, T[r], tail[r] * inv);
-                        R0[r] = fmaf(am, d0, R0[r]); R1[r] = fmaf(am, d1, R1[r]);
-                        R2[r] = fmaf(am, d2, R2[r]); RD[r] = fmaf(am, dD, RD[r]);
+                        const float dLda = fmaf(h, T[r], Q[r] * inv);
+                        Q[r] = fmaf(-h, w, Q[r]);
                         const float uu = og[r] * dLda;             // straight-through alpha clamp: o*G, not alpha
                         U0 += uu;
                         const float udy = uu * dy[r];
@@ -543,10 +545,11 @@ int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, BinView bv, I
     int nt = cam.Tx * (cam.row1 - cam.row0);
     if (nt <= 0) return 0;
     TgsProfScope prof(TGS_STAGE_RENDER_FWD, st);
+    TGS_CUDA(cudaMemsetAsync(bv.work_counter, 0, 2 * sizeof(uint32_t), st));
     k_render_fwd<<<nt, 256, 0, st>>>(bv.ranges, bv.records, cam.W, cam.H, cam.Tx, cam.row0, s->bg,
                                      s->depth_normalize, cam.alpha_max, out_color, out_depth, out_alpha, iv.final_T,
-                                     iv.n_contrib, iv.depth_raw, iv.color_acc, bv.ckpt, bv.slot_tile, touch_target,
-                                     residual_out);
+                                     iv.n_contrib, iv.depth_raw, iv.color_acc, bv.ckpt, bv.slot_tile, bv.ckpt_list,
+                                     bv.work_counter + 1, touch_target, residual_out);
     tgs_count_own(1);
     TGS_KERNEL_CHECK(st, s->debug);
     return 0;
@@ -566,7 +569,8 @@ int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, BinView bv, I
         if (mode != TGS_LOSS_NONE && ts == nullptr) { tgs_set_error("touch loss enabled but scale pointer is NULL"); return TGS_EINVAL; }
     }
     TgsProfScope prof(TGS_STAGE_RENDER_BWD, st);
-    // work units: two half tiles per tile (first segment) + two per 256-record checkpoint slot of the sorted list
+    // work units: two half tiles per tile (first segment) + two per checkpointed 256-record boundary (counted on the
+    // device by the forward); the grid is sized for the upper bound
     const int64_t slots = (num_rendered + 255) >> 8;
     const int64_t units = 2 * (int64_t)nt + 2 * slots;
     if (units > 0x7FFFFFFFll) { tgs_set_error("render backward: too many work units"); return TGS_EINVAL; }
@@ -585,7 +589,7 @@ int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, BinView bv, I
     TGS_CUDA(cudaMemsetAsync(bv.work_counter, 0, sizeof(uint32_t), st));
     k_render_bwd<<<(unsigned)grid, kBwdThreads, 0, st>>>(bv.ranges, bv.records, cam.W, cam.H, cam.Tx, cam.row0, s->bg,
                                      s->depth_normalize, cam.alpha_max, iv.final_T, iv.n_contrib, iv.depth_raw,
-                                     iv.color_acc, bv.ckpt, bv.slot_tile, bv.work_counter, 2 * nt, (int)units, dL_dcolor,
+                                     iv.color_acc, bv.ckpt, bv.slot_tile, bv.ckpt_list, bv.work_counter, 2 * nt, dL_dcolor,
                                      dL_ddepth, dL_dalpha, tt, tw, ts, tg, mode, tr0, tr1, residual, screen_grads);
     tgs_count_own(1);
     TGS_KERNEL_CHECK(st, s->debug);

@@ -67,11 +67,11 @@ struct BinView {
     TgsRecord* records;      // [I] packed, sorted
     void* cub_temp; size_t cub_temp_bytes;
     float* ckpt;             // [slots][5][256] forward checkpoints at 256-record boundaries of the tile lists
-    uint32_t* slot_tile;     // [slots] owning tile of the boundary in a slot, TGS_NO_TILE = none
-    uint32_t* work_counter;  // dynamic work-unit counter of the backward
+    uint32_t* slot_tile;     // [slots] owning tile of the boundary in a slot (valid for the slots in ckpt_list)
+    uint32_t* ckpt_list;     // [slots] slots the forward checkpointed, in completion order
+    uint32_t* work_counter;  // [0] dynamic work-unit counter of the backward, [1] length of ckpt_list
 };
 #define TGS_CKPT_FLOATS (5 * 256)
-#define TGS_NO_TILE 0xFFFFFFFFu
 struct ImageView {
     float* final_T; uint32_t* n_contrib; float* depth_raw;
     float* color_acc;        // [3][H*W] composited colour without the background term
