@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TGS_ABI_VERSION 4
+#define TGS_ABI_VERSION 5
 
 #define TGS_EINVAL   (-1)   /* bad argument combination / shape */
 #define TGS_ENOMEM   (-2)   /* allocator callback returned NULL */
@@ -138,9 +138,9 @@ void        tgs_launch_counts(uint64_t* own, uint64_t* cub);
  * the accumulated milliseconds and launch count since the last read, then resets.
  */
 #define TGS_STAGE_PREPROCESS      0
-#define TGS_STAGE_SCAN            1
-#define TGS_STAGE_DUPLICATE       2
-#define TGS_STAGE_SORT            3
+#define TGS_STAGE_SCAN            1   /* depth sort of the N Gaussians (CUB) */
+#define TGS_STAGE_DUPLICATE       2   /* per-chunk tile counts (k_bin_count) */
+#define TGS_STAGE_SORT            3   /* per-tile prefixes over the chunks + tile ranges (k_bin_prefix, k_bin_ranges) */
 #define TGS_STAGE_PACK            4
 #define TGS_STAGE_RENDER_FWD      5
 #define TGS_STAGE_LOSS_SCALE      6
@@ -151,7 +151,8 @@ void        tgs_launch_counts(uint64_t* own, uint64_t* cub);
 #define TGS_STAGE_ACTIVATE        11  /* activations forward + backward */
 #define TGS_STAGE_ADAM            12
 #define TGS_STAGE_REFINE          13  /* refine statistics + densify plan / apply */
-#define TGS_NUM_STAGES            14
+#define TGS_STAGE_BIN_SCATTER     14  /* ordered scatter of the Gaussian ids into the per-tile lists */
+#define TGS_NUM_STAGES            15
 int tgs_profile_enable(int32_t on);
 int tgs_profile_read(float* ms_per_stage, int32_t* launches_per_stage);
 
@@ -246,6 +247,16 @@ int tgs_fuse_touch_vision(const uint16_t* touch_mm, const uint16_t* vision_mm, c
                           uint16_t* fused_sigma_mm, float* target, float* weight, void* stream);
 
 /*
+ * SURVEY §8(f) N2 -- trainer-side decode of the on-disk touch maps: uint16 millimetre depth PNG -> fp32 target
+ * (mm * depth_unit; depth_unit = 1e-3 * pose scale: reference legacy/dataparser_tactile.py:65-66,229-235), uint16
+ * uncertainty PNG (sigma x 1000, reference utils/fuse_touch_vision.py:376,387) -> per-pixel weight
+ * (weight_mode 0: 1 [SIMPLE_LOSS]; 1: 1/(uw*sigma); 2: 1/(uw*sigma)^2; 0 where sigma == 0), uw = uncertainty_weight
+ * (reference scripts/train_bunny_real.sh:52).  Either output may be NULL.
+ */
+int tgs_decode_touch_maps(const uint16_t* depth_mm, const uint16_t* sigma_mm, int64_t num_pixels, float depth_unit,
+                          float uncertainty_weight, int32_t weight_mode, float* target, float* weight, void* stream);
+
+/*
  * Host-buffer entry point (the call a non-PyTorch trainer makes; timed by the end-to-end bench with
  * every host<->device copy inside the timed region).  EVERY pointer reachable from s_host / g_host /
  * grads_host and every *_host argument is a HOST pointer (NULL = absent / not wanted).  The call
@@ -266,27 +277,20 @@ typedef struct TgsGeomLayout {
     size_t records;           /* TgsRecord[N]: 3 x float4 = (x,y,depth,id) (A,B,C,opacity) (r,g,b,thr) */
     size_t cov3D;             /* float[N,6] */
     size_t tiles_touched;     /* uint32[N] */
-    size_t offsets;           /* uint32[N] inclusive scan of tiles_touched IN DEPTH ORDER */
     size_t clamped;           /* uint8[N] bit c = colour channel c clamped */
     size_t rect;              /* uint32[N,2]: (rminx | rmaxx<<16, rminy | rmaxy<<16) */
     size_t depth_keys;        /* uint32[N] bits(depth), 0xFFFFFFFF when nothing is emitted */
     size_t ids;               /* uint32[N] iota */
     size_t depth_keys_sorted; /* uint32[N] */
     size_t order;             /* uint32[N] Gaussian ids in ascending (depth, id) order */
-    size_t temp;              /* CUB temp for the depth sort / scan */
+    size_t span_sorted;       /* uint32[N,2]: `rect` of the Gaussians in that order ((0,0) = emits nothing) */
+    size_t temp;              /* CUB temp for the depth sort */
     size_t temp_bytes;
     size_t total;
 } TgsGeomLayout;
 typedef struct TgsBinningLayout {
-    size_t ranges;            /* uint32[T,2] */
     size_t records;           /* TgsRecord[I], depth-sorted per tile, contiguous */
-    size_t tile_sorted;       /* key_bytes x [I]: tile id of every sorted instance */
-    size_t vals_sorted;       /* uint32[I] Gaussian ids, final order */
-    size_t tile_unsorted;     /* key_bytes x [I] (emission order: depth-major) */
-    size_t vals_unsorted;     /* uint32[I] */
-    size_t sort_temp;
-    size_t sort_temp_bytes;
-    size_t key_bytes;         /* 2 when T <= 65536, else 4 */
+    size_t vals_sorted;       /* uint32[I] Gaussian ids, final (tile, depth, id) order */
     size_t ckpt;              /* float[slots][5][256]: per-pixel (T, r, g, b, D) composited BEFORE list position
                                * ranges[tile].x + 256k, written by the forward for every 256-record boundary it crosses;
                                * slot = that position >> 8 (unique per boundary).  Lets the backward replay a tile's list
@@ -302,10 +306,12 @@ typedef struct TgsImageLayout {
     size_t n_contrib;      /* uint32[H,W] */
     size_t depth_raw;      /* float[H,W] un-normalised sum depth*alpha*T */
     size_t color_acc;      /* float[3,H,W] composited colour WITHOUT the background term */
+    size_t ranges;         /* uint32[T,2]: per-tile [start, end) into the sorted instance list */
+    size_t count;          /* uint32[2]: num_rendered (device copy), 32-bit overflow flag */
     size_t total;
 } TgsImageLayout;
 int tgs_geom_layout(int32_t N, TgsGeomLayout* out);
-int tgs_binning_layout(int64_t num_rendered, int32_t num_tiles, TgsBinningLayout* out);
+int tgs_binning_layout(int64_t num_rendered, TgsBinningLayout* out);
 int tgs_image_layout(int32_t W, int32_t H, TgsImageLayout* out);
 
 /*

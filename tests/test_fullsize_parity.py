@@ -232,8 +232,9 @@ def test_emulated_peer_gather_is_bit_identical_to_summed_buffers(world):
 
 
 # ------------------------------------------------------------------------------------------------ (c)
-def test_uint32_tile_keys_path_vs_oracle():
-    """T = 257 x 257 = 66049 tiles (>= 65535): tile ids no longer fit 16 bits, the binning uses 32-bit tile keys."""
+def test_more_than_65535_tiles_multi_band_binning_vs_oracle():
+    """T = 257 x 257 = 66049 tiles: tile ids exceed 16 bits and the counting binning runs in 9 bands of 31 tile rows
+    (8192 cursors of shared memory per band)."""
     H = W = 4112
     deg, N = 1, 60000
     sc = synth.make_scene(N, deg, 0.004, 0.05, seed=12)
@@ -244,9 +245,6 @@ def test_uint32_tile_keys_path_vs_oracle():
         bins = O.bin_and_sort(pre, S)
     rs = cuda_settings(cam, deg, DEV)
     m, s, r, o, sh = [t.to(DEV) for t in (sc.means3D, sc.scales, sc.rotations, sc.opacities, sc.shs)]
-    lay = T._lib.TgsBinningLayout()
-    T._lib.load().tgs_binning_layout(1000, 257 * 257, C.byref(lay))
-    assert lay.key_bytes == 4
     st = T.inspect_state.forward_state(m, o, rs, shs=sh, scales=s, rotations=r)
     assert int(st["tile_ids"].max()) >= 65536, "scene does not reach tile ids above 16 bits"
     assert torch.equal(st["radii"].cpu(), pre.radii)

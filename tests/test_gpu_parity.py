@@ -68,7 +68,7 @@ def test_preprocess_and_binning_bit_exact(name):
     assert torch.equal(st["tiles_touched"].cpu(), pre.tiles_touched)
     assert torch.equal(st["rect_min"].cpu()[vis], pre.rect_min[vis])
     assert torch.equal(st["rect_max"].cpu()[vis], pre.rect_max[vis])
-    assert st["num_rendered"] == bins.keys.numel() == int(st["offsets"].cpu().long().max() if st["offsets"].numel() else 0)
+    assert st["num_rendered"] == bins.keys.numel() == st["num_rendered_device"]
     # depth order of the Gaussians (phase 1 of the two-phase sort): ascending (depth bits, id) over emitters
     dk = torch.where(pre.tiles_touched > 0, pre.depth.detach().contiguous().view(torch.int32).long() & 0xFFFFFFFF,
                      torch.full_like(pre.radii, 0xFFFFFFFF, dtype=torch.int64))
@@ -78,11 +78,11 @@ def test_preprocess_and_binning_bit_exact(name):
     assert torch.equal(bits(st["gdepth"].cpu()[vis]), bits(pre.depth[vis]))
     assert torch.equal(bits(st["conic"].cpu()[vis]), bits(pre.conic[vis]))
     assert torch.equal(bits(st["cov3D"].cpu()), bits(pre.cov3D))
-    # emission order is an implementation detail (depth-major here, Gaussian-major in the oracle): the
-    # emitted MULTISET and the final sorted list are what the spec pins
-    emitted = (st["tile_ids_emitted"].cpu() << 32) | st["vals_emitted"].cpu().long()
+    # no per-instance keys are ever emitted or sorted (binning.cu counts rectangles): the final sorted list and the
+    # tile ranges are what the spec pins; as a multiset the list must equal the oracle's Gaussian-major emission
+    listed = (st["tile_ids"].cpu() << 32) | st["vals"].cpu().long()
     ref_emitted = ((bins.keys_unsorted >> 32) << 32) | bins.vals_unsorted.long()
-    assert torch.equal(torch.sort(emitted).values, torch.sort(ref_emitted).values)
+    assert torch.equal(torch.sort(listed).values, torch.sort(ref_emitted).values)
     assert torch.equal(st["keys"].cpu(), bins.keys)
     assert torch.equal(st["vals"].cpu(), bins.vals)
     assert torch.equal(st["ranges"].cpu(), bins.ranges)
@@ -468,12 +468,21 @@ def test_fullsize_integer_invariants(c3_state):
     cfg, cam, rs, (m, s, r, o, sh) = c3_state
     st = T.inspect_state.forward_state(m, o, rs, shs=sh, scales=s, rotations=r)
     I = st["num_rendered"]
-    assert I == int(st["tiles_touched"].long().sum()) == int(st["offsets"].long().max()) > 1_000_000
+    assert I == int(st["tiles_touched"].long().sum()) == st["num_rendered_device"] > 1_000_000
     keys = st["keys"]
     assert bool((keys[1:] >= keys[:-1]).all()), "sorted keys not monotone"
-    em = (st["tile_ids_emitted"] << 32) | st["vals_emitted"].long()
+    # the list as a multiset == every (tile of its rectangle, Gaussian) pair exactly once
     fin = (st["tile_ids"] << 32) | st["vals"].long()
-    assert torch.equal(torch.sort(em).values, torch.sort(fin).values), "sort changed the multiset of instances"
+    vis_ids = torch.nonzero(st["tiles_touched"] > 0).flatten()
+    x0, y0 = st["rect_min"][vis_ids, 0].long(), st["rect_min"][vis_ids, 1].long()
+    w = st["rect_max"][vis_ids, 0].long() - x0
+    cnt = st["tiles_touched"][vis_ids].long()
+    gid = torch.repeat_interleave(vis_ids, cnt)
+    loc = torch.arange(I, device=gid.device) - torch.repeat_interleave(torch.cumsum(cnt, 0) - cnt, cnt)
+    ww, xx0, yy0 = (torch.repeat_interleave(t, cnt) for t in (w, x0, y0))
+    Tx = (cfg["W"] + 15) // 16
+    em = (((yy0 + loc // ww) * Tx + xx0 + loc % ww) << 32) | gid
+    assert torch.equal(torch.sort(em).values, torch.sort(fin).values), "the list is not the multiset of rectangle instances"
     same = keys[1:] == keys[:-1]
     assert bool((st["vals"][1:][same] >= st["vals"][:-1][same]).all()), "sort not stable"
     rg = st["ranges"].long()

@@ -8,9 +8,9 @@ the hyphen); use ``import touchgs_b200`` (top-level shim) or ``import diff_gauss
 from . import _lib
 from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, TouchOptions,
                          rasterize_gaussians, _RasterizeGaussians)
-from . import synth, sharding, inspect_state, touch_inputs, refstructure, train_step
+from . import synth, sharding, inspect_state, touch_inputs, refstructure, train_step, dataset
 from .train_step import TouchGSTrainer, TrainConfig, photometric_loss, adam_step, activate, densify
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "TouchOptions", "rasterize_gaussians",
-           "synth", "sharding", "inspect_state", "touch_inputs", "refstructure", "train_step", "TouchGSTrainer", "TrainConfig", "photometric_loss",
+           "synth", "sharding", "inspect_state", "touch_inputs", "dataset", "refstructure", "train_step", "TouchGSTrainer", "TrainConfig", "photometric_loss",
            "adam_step", "activate", "densify", "_lib"]

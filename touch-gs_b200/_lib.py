@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TGS_LIB_PATH") or os.path.join(HERE, "libtgs.so")   # override: A/B builds
 
-TGS_ABI_VERSION = 4
+TGS_ABI_VERSION = 5
 BUF_GEOM, BUF_BINNING, BUF_IMAGE, BUF_TEMP = 0, 1, 2, 3
 LOSS_NONE, LOSS_L1, LOSS_L2 = 0, 1, 2
 LOSS_MODES = {"none": LOSS_NONE, "l1": LOSS_L1, "l2": LOSS_L2}
@@ -60,18 +60,17 @@ class TgsGrads(C.Structure):
 
 class TgsGeomLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in
-                ("records", "cov3D", "tiles_touched", "offsets", "clamped", "rect", "depth_keys", "ids",
-                 "depth_keys_sorted", "order", "temp", "temp_bytes", "total")]
+                ("records", "cov3D", "tiles_touched", "clamped", "rect", "depth_keys", "ids",
+                 "depth_keys_sorted", "order", "span_sorted", "temp", "temp_bytes", "total")]
 
 
 class TgsBinningLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in
-                ("ranges", "records", "tile_sorted", "vals_sorted", "tile_unsorted", "vals_unsorted",
-                 "sort_temp", "sort_temp_bytes", "key_bytes", "ckpt", "slot_tile", "ckpt_list", "work_counter", "slots", "total")]
+                ("records", "vals_sorted", "ckpt", "slot_tile", "ckpt_list", "work_counter", "slots", "total")]
 
 
 class TgsImageLayout(C.Structure):
-    _fields_ = [(n, C.c_size_t) for n in ("final_T", "n_contrib", "depth_raw", "color_acc", "total")]
+    _fields_ = [(n, C.c_size_t) for n in ("final_T", "n_contrib", "depth_raw", "color_acc", "ranges", "count", "total")]
 
 
 class TgsRefBinningLayout(C.Structure):
@@ -123,11 +122,12 @@ SIGNATURES = {
                                        c_fp]),
     "tgs_fuse_touch_vision": (C.c_int, [c_fp, c_fp, c_fp, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_int32,
                                         C.c_double, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "tgs_decode_touch_maps": (C.c_int, [c_fp, c_fp, C.c_int64, C.c_float, C.c_float, C.c_int32, c_fp, c_fp, c_fp]),
     "tgs_train_step_host": (C.c_int, [C.POINTER(TgsSettings), C.POINTER(TgsGaussians), c_fp, c_fp, c_fp,
                                       C.c_int32, C.c_float, C.POINTER(TgsGrads), c_fp, c_fp, c_fp, c_fp,
                                       C.POINTER(C.c_int64), c_fp]),
     "tgs_geom_layout": (C.c_int, [C.c_int32, C.POINTER(TgsGeomLayout)]),
-    "tgs_binning_layout": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(TgsBinningLayout)]),
+    "tgs_binning_layout": (C.c_int, [C.c_int64, C.POINTER(TgsBinningLayout)]),
     "tgs_image_layout": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(TgsImageLayout)]),
     "tgs_photometric_scratch_floats": (C.c_size_t, [C.c_int32, C.c_int32]),
     "tgs_photometric_loss_forward": (C.c_int, [c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
@@ -196,7 +196,7 @@ def check(rc: int, what: str) -> None:
 
 
 STAGES = ("preprocess", "scan", "duplicate", "sort", "pack", "render_fwd", "loss_scale", "render_bwd",
-          "preprocess_bwd", "photo_fwd", "photo_bwd", "activate", "adam", "refine")
+          "preprocess_bwd", "photo_fwd", "photo_bwd", "activate", "adam", "refine", "bin_scatter")
 
 
 def profile_enable(on: bool) -> None:

@@ -85,29 +85,22 @@ extern "C" int tgs_geom_layout(int32_t N, TgsGeomLayout* o) {
     o->records = c.take(n * sizeof(TgsRecord));
     o->cov3D = c.take(n * 6 * sizeof(float));
     o->tiles_touched = c.take(n * sizeof(uint32_t));
-    o->offsets = c.take(n * sizeof(uint32_t));
     o->clamped = c.take(n);
     o->rect = c.take(n * sizeof(uint2));
     o->depth_keys = c.take(n * sizeof(uint32_t));
     o->ids = c.take(n * sizeof(uint32_t));
     o->depth_keys_sorted = c.take(n * sizeof(uint32_t));
     o->order = c.take(n * sizeof(uint32_t));
+    o->span_sorted = c.take(n * sizeof(uint2));
     o->temp_bytes = tgs_depth_sort_temp_bytes(N > 0 ? N : 1);
     o->temp = c.take(o->temp_bytes);
     o->total = c.off > 0 ? c.off : TGS_ALIGN;
     return 0;
 }
-extern "C" int tgs_binning_layout(int64_t I, int32_t T, TgsBinningLayout* o) {
+extern "C" int tgs_binning_layout(int64_t I, TgsBinningLayout* o) {
     Carver c; size_t n = (size_t)(I > 0 ? I : 0);
-    o->key_bytes = T < 65535 ? 2 : 4;
-    o->ranges = c.take((size_t)(T > 0 ? T : 1) * sizeof(uint2));
     o->records = c.take(n * sizeof(TgsRecord));
-    o->tile_sorted = c.take(n * o->key_bytes);
     o->vals_sorted = c.take(n * sizeof(uint32_t));
-    o->tile_unsorted = c.take(n * o->key_bytes);
-    o->vals_unsorted = c.take(n * sizeof(uint32_t));
-    o->sort_temp_bytes = tgs_tile_sort_temp_bytes(I > 0 ? I : 1, T);
-    o->sort_temp = c.take(o->sort_temp_bytes);
     o->slots = (n >> 8) + 2;
     o->ckpt = c.take(o->slots * TGS_CKPT_FLOATS * sizeof(float));
     o->slot_tile = c.take(o->slots * sizeof(uint32_t));
@@ -122,6 +115,9 @@ extern "C" int tgs_image_layout(int32_t W, int32_t H, TgsImageLayout* o) {
     o->n_contrib = c.take(p * 4);
     o->depth_raw = c.take(p * 4);
     o->color_acc = c.take(p * 12);
+    const size_t T = (size_t)((W + TGS_TILE - 1) / TGS_TILE) * (size_t)((H + TGS_TILE - 1) / TGS_TILE);
+    o->ranges = c.take((T > 0 ? T : 1) * sizeof(uint2));
+    o->count = c.take(2 * sizeof(uint32_t));
     o->total = c.off;
     return 0;
 }
@@ -130,20 +126,18 @@ GeomView tgs_geom_view(void* base, int N) {
     TgsGeomLayout l; tgs_geom_layout(N, &l);
     char* b = (char*)base; GeomView v;
     v.records = (TgsRecord*)(b + l.records); v.cov3D = (float*)(b + l.cov3D);
-    v.tiles_touched = (uint32_t*)(b + l.tiles_touched); v.offsets = (uint32_t*)(b + l.offsets);
+    v.tiles_touched = (uint32_t*)(b + l.tiles_touched);
     v.clamped = (uint8_t*)(b + l.clamped); v.rect = (uint2*)(b + l.rect);
     v.depth_keys = (uint32_t*)(b + l.depth_keys); v.ids = (uint32_t*)(b + l.ids);
     v.depth_keys_sorted = (uint32_t*)(b + l.depth_keys_sorted); v.order = (uint32_t*)(b + l.order);
+    v.span_sorted = (uint2*)(b + l.span_sorted);
     v.temp = b + l.temp; v.temp_bytes = l.temp_bytes;
     return v;
 }
-BinView tgs_bin_view(void* base, int64_t I, int T) {
-    TgsBinningLayout l; tgs_binning_layout(I, T, &l);
+BinView tgs_bin_view(void* base, int64_t I) {
+    TgsBinningLayout l; tgs_binning_layout(I, &l);
     char* b = (char*)base; BinView v;
-    v.ranges = (uint2*)(b + l.ranges); v.records = (TgsRecord*)(b + l.records);
-    v.tile_sorted = b + l.tile_sorted; v.vals_sorted = (uint32_t*)(b + l.vals_sorted);
-    v.tile_unsorted = b + l.tile_unsorted; v.vals_unsorted = (uint32_t*)(b + l.vals_unsorted);
-    v.cub_temp = b + l.sort_temp; v.cub_temp_bytes = l.sort_temp_bytes;
+    v.records = (TgsRecord*)(b + l.records); v.vals_sorted = (uint32_t*)(b + l.vals_sorted);
     v.ckpt = (float*)(b + l.ckpt); v.slot_tile = (uint32_t*)(b + l.slot_tile);
     v.ckpt_list = (uint32_t*)(b + l.ckpt_list);
     v.work_counter = (uint32_t*)(b + l.work_counter);
@@ -154,6 +148,7 @@ ImageView tgs_image_view(void* base, int W, int H) {
     char* b = (char*)base; ImageView v;
     v.final_T = (float*)(b + l.final_T); v.n_contrib = (uint32_t*)(b + l.n_contrib);
     v.depth_raw = (float*)(b + l.depth_raw); v.color_acc = (float*)(b + l.color_acc);
+    v.ranges = (uint2*)(b + l.ranges); v.count = (uint32_t*)(b + l.count);
     return v;
 }
 
@@ -161,7 +156,8 @@ ImageView tgs_image_view(void* base, int W, int H) {
 static int check_inputs(const TgsSettings* s, const TgsGaussians* g) {
     if (!s || !g) { tgs_set_error("NULL settings / gaussians"); return TGS_EINVAL; }
     if (s->image_width <= 0 || s->image_height <= 0) { tgs_set_error("bad image size %dx%d", s->image_width, s->image_height); return TGS_EINVAL; }
-    if (s->image_width > 65535 * TGS_TILE || s->image_height > 65535 * TGS_TILE) { tgs_set_error("image too large"); return TGS_EINVAL; }
+    if (s->image_width > TGS_BIN_BAND_TILES * TGS_TILE || s->image_height > 65535 * TGS_TILE) {
+        tgs_set_error("image too large (width <= %d, height <= %d)", TGS_BIN_BAND_TILES * TGS_TILE, 65535 * TGS_TILE); return TGS_EINVAL; }
     if (g->N < 0) { tgs_set_error("negative N"); return TGS_EINVAL; }
     if (!s->viewmatrix || !s->projmatrix || !s->bg) { tgs_set_error("viewmatrix / projmatrix / bg must be non-NULL"); return TGS_EINVAL; }
     if (g->N > 0) {
@@ -230,38 +226,50 @@ extern "C" int tgs_forward(const TgsSettings* s, const TgsGaussians* g, tgs_allo
     if ((touch_target == nullptr) != (residual_out == nullptr)) { tgs_set_error("touch_target and residual_out go together"); return TGS_EINVAL; }
     int64_t I = 0, cap = 0;
     void* binning = nullptr;
+    void* temp = nullptr;
     uint32_t* hp = pinned_word();
     if (!hp) { tgs_set_error("cudaHostAlloc failed"); return TGS_ENOMEM; }
-    auto tail = [&](int64_t count, int64_t capacity, bool spec) -> int {      // bin + render for `capacity` slots
-        TgsBinningLayout bl; tgs_binning_layout(capacity, T, &bl);
+    auto tail = [&](int64_t count, int64_t capacity, bool spec) -> int {      // scatter + pack + render for `capacity` slots
+        TgsBinningLayout bl; tgs_binning_layout(capacity, &bl);
         binning = alloc(user, TGS_BUF_BINNING, bl.total);
         if (!binning) { tgs_set_error("allocator returned NULL"); return TGS_ENOMEM; }
-        BinView bv = tgs_bin_view(binning, capacity, T);
-        int r = tgs_emit_sort_pack(gv, bv, N, count, capacity, spec, T, cam.Tx, st); if (r) return r;
+        BinView bv = tgs_bin_view(binning, capacity);
+        int r = tgs_bin_scatter_pack(gv, bv, N, count, capacity, spec, cam.Tx, cam.Ty, temp, iv.ranges, iv.count, st); if (r) return r;
         if (s->debug) TGS_CUDA(cudaStreamSynchronize(st));
-        return tgs_launch_render_fwd(cam, s, bv, iv, out_color, out_depth, out_alpha, touch_target, residual_out, st);
+        return tgs_launch_render_fwd(cam, s, bv, iv, capacity, out_color, out_depth, out_alpha, touch_target, residual_out, st);
+    };
+    auto read_count = [&]() -> int {                    // hp[0] = num_rendered, hp[1] = 32-bit overflow flag
+        if (hp[1]) { tgs_set_error("num_rendered does not fit 32 bits (more than 4,294,967,295 tile instances)"); return TGS_EINVAL; }
+        I = (int64_t)hp[0];
+        return 0;
     };
     if (N > 0) {
+        const size_t tb = tgs_bin_temp_bytes(N, cam.Tx, cam.Ty);
+        temp = alloc(user, TGS_BUF_TEMP, tb);
+        if (!temp) { tgs_set_error("allocator returned NULL"); return TGS_ENOMEM; }
         rc = tgs_launch_preprocess(cam, s, g, gv, radii, st); if (rc) return rc;
-        rc = tgs_depth_order_and_scan(gv, N, st); if (rc) return rc;
-        TGS_CUDA(cudaMemcpyAsync(hp, gv.offsets + (N - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        rc = tgs_depth_order(gv, N, st); if (rc) return rc;
+        rc = tgs_bin_count(gv, N, cam.Tx, cam.Ty, temp, iv.ranges, iv.count, st); if (rc) return rc;
+        TGS_CUDA(cudaMemcpyAsync(hp, iv.count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         if (s->rendered_hint > 0) {
-            // SPECULATIVE: enqueue binning + render for `hint` slots, THEN wait for the count (event recorded
-            // right after the scan: the GPU keeps working on the speculative tail while the host wakes up)
+            // SPECULATIVE: enqueue scatter + pack + render for `hint` slots, THEN wait for the count (event recorded
+            // right after the count kernels: the GPU keeps working on the speculative tail while the host wakes up)
             cudaEvent_t ev = count_event();
             if (!ev) { tgs_set_error("cudaEventCreate failed"); return TGS_ENOMEM; }
             TGS_CUDA(cudaEventRecord(ev, st));
             cap = s->rendered_hint;
             rc = tail(cap, cap, true); if (rc) return rc;
             TGS_CUDA(cudaEventSynchronize(ev));
-            I = (int64_t)*hp;
+            rc = read_count(); if (rc) return rc;
             if (I > cap) { cap = I; rc = tail(I, I, false); if (rc) return rc; }   // hint too small: exact re-run
         } else {
             TGS_CUDA(cudaStreamSynchronize(st));   // the one host sync of the forward
-            I = (int64_t)*hp; cap = I;
+            rc = read_count(); if (rc) return rc;
+            cap = I;
             rc = tail(I, I, false); if (rc) return rc;
         }
     } else {
+        rc = tgs_bin_count(gv, 0, cam.Tx, cam.Ty, nullptr, iv.ranges, iv.count, st); if (rc) return rc;
         rc = tail(0, 0, false); if (rc) return rc;
     }
     saved->geom = geom; saved->binning = binning; saved->image = image; saved->num_rendered = I; saved->capacity = cap;
@@ -277,7 +285,7 @@ extern "C" int tgs_backward_render(const TgsSettings* s, const TgsGaussians* g, 
     if (!dL_dcolor || (g->N > 0 && !screen_grads)) { tgs_set_error("tgs_backward_render: NULL gradient buffers"); return TGS_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
     const TgsCam cam = tgs_make_cam(s);
-    BinView bv = tgs_bin_view(saved->binning, saved->capacity > 0 ? saved->capacity : saved->num_rendered, cam.Tx * cam.Ty);
+    BinView bv = tgs_bin_view(saved->binning, saved->capacity > 0 ? saved->capacity : saved->num_rendered);
     ImageView iv = tgs_image_view(saved->image, cam.W, cam.H);
     if (g->N > 0) TGS_CUDA(cudaMemsetAsync(screen_grads, 0, sizeof(float) * TGS_NGRAD * (size_t)g->N, st));
     return tgs_launch_render_bwd(cam, s, bv, iv, saved->num_rendered, dL_dcolor, dL_ddepth, dL_dalpha, touch, residual_out,

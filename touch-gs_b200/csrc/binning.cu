@@ -1,112 +1,332 @@
-// binning.cu -- tile binning of the visible Gaussians.
+// binning.cu -- tile binning of the visible Gaussians, hand-written end to end except the
+// depth sort of the N Gaussians.
 //
-// The spec'd RESULT is the list of (tile, Gaussian) instances sorted by the 64-bit key
-// (tile << 32 | bits(depth)), ties in ascending Gaussian id (stable sort of a Gaussian-major emission),
-// plus one [start,end) range per tile.  We produce exactly that list (bit-exact against
-// oracle/gs_oracle.py::bin_and_sort) with a cheaper TWO-PHASE sort:
-//   1. radix-sort the N Gaussians once by depth bits (32-bit keys, N items; stable => equal depths keep
-//      ascending id; invisible Gaussians get key 0xFFFFFFFF and emit nothing);
-//   2. scan tiles_touched in that depth order, emit the instances depth-major (warp-cooperative,
-//      coalesced) with the TILE ID as the only key (16 bits when T <= 65536);
-//   3. stable radix sort of I (tile, id) pairs over ceil(log2 T) bits: 2 onesweep passes on 6-byte pairs
-//      instead of 6 passes on 12-byte pairs.  Stability carries the depth order into every tile.
-//   4. fused tile-range detection + packing of the sorted 48-byte records (gather -> shared memory ->
-//      one TMA bulk store per 256 records, so the packed array is written with full-line stores).
-// The scans / sorts are CUB device primitives (library code, like cuBLAS for a plain GEMM).
+// The spec'd RESULT is the list of (tile, Gaussian) instances sorted by the 64-bit key (tile << 32 | bits(depth)),
+// ties in ascending Gaussian id (stable sort of a Gaussian-major emission), plus one [start,end) range per tile.
+// We produce exactly that list (bit-exact against oracle/gs_oracle.py::bin_and_sort) WITHOUT ever materialising or
+// sorting per-instance keys.  Every instance of a Gaussian comes from its tile RECTANGLE, so the position of
+// instance (g, t) in the final list is
+//       ranges[t].x + #{ g' before g in (depth, id) order : t in rect(g') },
+// a counting problem over rectangles:
+//   0. radix-sort the N Gaussians once by depth bits (CUB, 32-bit keys, N items; stable => equal depths keep
+//      ascending id; Gaussians that emit nothing get key 0xFFFFFFFF) -> `order`;
+//   1. k_bin_count: the depth order is cut into chunks of C Gaussians; one CTA per chunk counts how many of the
+//      chunk's rectangles cover each tile (4 corner updates per rectangle into a shared-memory difference array +
+//      a 2-D prefix sum) and writes its row of the [chunks x T] count matrix;
+//   2. k_bin_prefix: per tile column, exclusive prefix over the chunks (in place) + the column total;
+//      k_bin_ranges: exclusive scan of the totals -> ranges[t] and num_rendered (64-bit, overflow-checked);
+//   3. k_bin_scatter: one WARP per chunk loads its row (+ the tile starts) into shared memory as per-tile cursors and
+//      walks its C Gaussians IN ORDER; the lanes take the tiles of the current Gaussian's rectangle, bump the cursors
+//      and write the Gaussian id to its final position.  Order inside a tile = order of the walk = depth order.
+//   4. k_pack: gather of the sorted 48-byte records -> shared memory -> one TMA bulk store per 256 records, so that
+//      every tile's list is one contiguous run the compositing kernels can stage with TMA bulk loads.
+// Tiles are processed in bands of tile rows (count: <= 8192 tiles = 32 KB of counters per CTA; scatter: ~1024 tiles
+// per single-warp unit) so any image size fits.
+//
+// Replaces: emission of (tile id, Gaussian id) pairs + two CUB onesweep passes over I pairs + boundary detection
+// (0.048 + 0.190 ms at c3, and 12 B/instance of key/value traffic per pass) by three small kernels over N Gaussians.
 // Roofline: HBM.  Algorithmic bytes per instance: key/val write 12, sort 24, range detect 8,
-// record gather 48 + write 48 (we move 6-byte pairs, so real traffic is below the algorithmic figure).
+// record gather 48 + write 48; what actually moves: 4 B (id) written once + the 96 B of the record pack, plus
+// 12 B x chunks x T of count-matrix traffic (0.1 GB at c3).
 #include "tgs_common.cuh"
 #include <cub/cub.cuh>
 
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kCountCells = 16384;      // 64 KB difference array per count CTA (c3: 69 x 121 cells = 33 KB, one band)
 
-struct TilesInOrder {
-    const uint32_t* tiles; const uint32_t* order;
-    __device__ __forceinline__ uint32_t operator()(uint32_t r) const { return tiles[order[r]]; }
+struct Bands { int rows; int n; int tiles; };   // tile rows per band, number of bands, rows * Tx
+struct Plan {
+    int chunk;           // Gaussians per chunk (depth ranks)
+    int nchunks;
+    Bands count;         // k_bin_count: wide bands (<= TGS_BIN_BAND_TILES tiles of shared-memory counters per CTA)
+    Bands scatter;       // k_bin_scatter: narrow bands -- the walk of a (chunk, band) unit is sequential, so many small
+                         // units (a few tile rows, ~4 KB of cursors, 30+ resident warps per SM) beat few large ones
 };
-using TilesIt = cub::TransformInputIterator<uint32_t, TilesInOrder, cub::CountingInputIterator<uint32_t>>;
+Bands make_bands(int max_tiles, int Tx, int Ty) {
+    Bands b;
+    b.rows = max_tiles / Tx;
+    if (b.rows < 1) b.rows = 1;
+    if (b.rows > Ty) b.rows = Ty;
+    b.n = (Ty + b.rows - 1) / b.rows;
+    b.tiles = b.rows * Tx;
+    return b;
+}
+Plan make_plan(int N, int Tx, int Ty) {
+    Plan p;
+    p.chunk = 1024;
+    while (p.chunk < 8192 && (N + p.chunk - 1) / p.chunk > 1536) p.chunk *= 2;
+    p.nchunks = (N + p.chunk - 1) / p.chunk;
+    if (p.nchunks < 1) p.nchunks = 1;
+    // count kernel: a (rows + 1) x (Tx + 1) difference array of int32 in shared memory, <= kCountCells cells
+    p.count.rows = kCountCells / (Tx + 1) - 1;
+    if (p.count.rows < 1) p.count.rows = 1;
+    if (p.count.rows > Ty) p.count.rows = Ty;
+    p.count.n = (Ty + p.count.rows - 1) / p.count.rows;
+    p.count.tiles = (p.count.rows + 1) * (Tx + 1);       // cells, not tiles
+    p.scatter = make_bands(TGS_BIN_SCATTER_TILES, Tx, Ty);
+    return p;
+}
 
-// Emission in depth order.  One warp per 32 consecutive depth ranks.  The scan makes the instances of those 32
-// Gaussians ONE contiguous output range [B, E), so the warp walks that range 32 slots at a time -- every store is a
-// full coalesced line -- and each lane finds the Gaussian that owns its slot by a 5-step binary search over the 32
-// inclusive offsets held one per lane (shuffles), instead of the warp serialising over its Gaussians with a third of
-// the lanes busy.
-template <typename KeyT>
+// the part of a Gaussian's tile rectangle inside tile rows [r0, r1)
+struct RectClip { uint32_t x0, w, y0, h; };
+__device__ __forceinline__ RectClip clip_rect(uint2 rc, int r0, int r1) {
+    RectClip c;
+    c.x0 = rc.x & 0xFFFF; c.w = (rc.x >> 16) - c.x0;
+    int y0 = (int)(rc.y & 0xFFFF), y1 = (int)(rc.y >> 16);
+    y0 = max(y0, r0); y1 = min(y1, r1);
+    c.y0 = (uint32_t)y0; c.h = y1 > y0 ? (uint32_t)(y1 - y0) : 0u;
+    return c;
+}
+// l / w for l < 2^32 with a precomputed m = floor(2^32 / w): the estimate is at most 1 too small
+__device__ __forceinline__ uint32_t div_by(uint32_t l, uint32_t w, uint32_t m, uint32_t& rem) {
+    uint32_t q = w == 1 ? l : __umulhi(l, m);
+    rem = l - q * w;
+    if (rem >= w) { ++q; rem -= w; }
+    return q;
+}
+__device__ __forceinline__ uint32_t magic_of(uint32_t w) { return w > 1 ? (uint32_t)(0x100000000ull / w) : 0u; }
+
+// ---- 1. per-chunk tile counts.  grid (nchunks, nbands), 256 threads.
+// A rectangle adds 1 to every tile it covers; instead of one shared-memory atomic per covered tile (I of them) each
+// rectangle posts FOUR signed corner updates into a (rows+1) x (Tx+1) difference array, and a 2-D prefix sum (along
+// x by warp scans, along y by one thread per column, fused with the write of the chunk's row of the count matrix)
+// turns them into coverage counts: 4 atomics per Gaussian instead of ~11 (c3) / ~33 (c5).
 __global__ void __launch_bounds__(256)
-k_emit(int N, const uint32_t* __restrict__ order, const uint32_t* __restrict__ tiles,
-       const uint32_t* __restrict__ offsets, const uint2* __restrict__ rect, int Tx, uint32_t cap,
-       KeyT* __restrict__ keys, uint32_t* __restrict__ vals) {
-    const int lane = threadIdx.x & 31;
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;          // depth rank
-    const int r_first = r - lane;
-    if (r_first >= N) return;
-    const int r_last = min(r_first + 31, N - 1);
-    // inclusive offset of this lane's rank (lanes past N repeat the last one: they own nothing)
-    const uint32_t end = offsets[min(r, r_last)];
-    uint32_t id = 0, cnt = 0;
-    uint2 rc = make_uint2(0, 0);
-    if (r < N) {
-        id = order[r];
-        cnt = tiles[id];
-        if (cnt) rc = rect[id];
-    }
-    const uint32_t base = end - cnt;                               // exclusive offset of this lane's Gaussian
-    const uint32_t B = __shfl_sync(kFull, base, 0);
-    const uint32_t E = __shfl_sync(kFull, end, 31);
-    for (uint32_t p0 = B; p0 < E; p0 += 32) {
-        const uint32_t p = p0 + lane;
-        // owner = number of lanes whose inclusive offset is <= p (offsets are monotone)
-        int own = 0;
-#pragma unroll
-        for (int s = 16; s >= 1; s >>= 1) {
-            const uint32_t e = __shfl_sync(kFull, end, own + s - 1);
-            if (e <= p) own += s;
+k_bin_count(int N, int chunk, const uint32_t* __restrict__ order, const uint32_t* __restrict__ tiles,
+            const uint2* __restrict__ rect, int Tx, int Ty, int rows_per_band, int T, uint32_t* __restrict__ cnt,
+            uint2* __restrict__ span_sorted) {
+    extern __shared__ int diff[];                      // [(rows+1)][Tx+1]
+    const int band = blockIdx.y;
+    const int r0 = band * rows_per_band, r1 = min(Ty, r0 + rows_per_band);
+    const int rows = r1 - r0, S = Tx + 1;
+    for (int t = threadIdx.x; t < (rows + 1) * S; t += 256) diff[t] = 0;
+    __syncthreads();
+    const int first = blockIdx.x * chunk, last = min(N, first + chunk);
+    for (int r = first + threadIdx.x; r < last; r += 256) {
+        const uint32_t id = order[r];
+        uint2 rc = make_uint2(0u, 0u);
+        if (tiles[id]) {
+            rc = rect[id];
+            const RectClip c = clip_rect(rc, r0, r1);
+            if (c.w && c.h) {
+                const int y0 = (int)c.y0 - r0, x0 = (int)c.x0;
+                atomicAdd(&diff[y0 * S + x0], 1);
+                atomicAdd(&diff[y0 * S + x0 + (int)c.w], -1);
+                atomicAdd(&diff[(y0 + (int)c.h) * S + x0], -1);
+                atomicAdd(&diff[(y0 + (int)c.h) * S + x0 + (int)c.w], 1);
+            }
         }
-        own = min(own, 31);
-        const uint32_t gbase = __shfl_sync(kFull, base, own);
-        const uint32_t gid = __shfl_sync(kFull, id, own);
-        const uint32_t rx = __shfl_sync(kFull, rc.x, own), ry = __shfl_sync(kFull, rc.y, own);
-        if (p < E && p < cap) {                                    // speculative mode: never write past the hint
-            const uint32_t x0 = rx & 0xFFFF, w = (rx >> 16) - x0, y0 = ry & 0xFFFF;
-            const uint32_t t = p - gbase;
-            const uint32_t yy = t / w, xx = t - yy * w;            // row-major: y outer, x inner
-            keys[p] = (KeyT)((y0 + yy) * Tx + x0 + xx);
-            vals[p] = gid;
+        // the rectangles in DEPTH ORDER (empty = (0,0)): the scatter walks them with coalesced loads
+        if (band == 0) span_sorted[r] = rc;
+    }
+    __syncthreads();
+    {   // prefix along x: one warp per row
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int y = warp; y < rows; y += 8) {
+            int carry = 0;
+            for (int c0 = 0; c0 < Tx; c0 += 32) {
+                const int x = c0 + lane;
+                int v = x < Tx ? diff[y * S + x] : 0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int n = __shfl_up_sync(kFull, v, o);
+                    if (lane >= o) v += n;
+                }
+                v += carry;
+                if (x < Tx) diff[y * S + x] = v;
+                carry = __shfl_sync(kFull, v, 31);
+            }
+        }
+    }
+    __syncthreads();
+    // prefix along y, one thread per column, written straight to the chunk's row of the count matrix
+    uint32_t* row = cnt + (size_t)blockIdx.x * T + (size_t)r0 * Tx;
+    for (int x = threadIdx.x; x < Tx; x += 256) {
+        int run = 0;
+        for (int y = 0; y < rows; ++y) {
+            run += diff[y * S + x];
+            row[(size_t)y * Tx + x] = (uint32_t)run;
         }
     }
 }
 
-// Fused A4 + record packing.  256 instances per CTA: each thread gathers its instance's 48-byte record
-// (3 x LDG.128, mostly L2 hits: the per-Gaussian record array is 48 MB at 1M splats) into shared memory,
-// performs the tile-boundary test of identifyTileRanges, and one thread writes the 12 KB block back with
-// a single TMA bulk store.
-template <typename KeyT>
+// ---- 2a. per tile column: exclusive prefix over the chunks (in place) and the column total.
+// CTA = 32 tile columns x 8 chunk slices (a warp reads one 128-byte row segment per chunk).
 __global__ void __launch_bounds__(256)
-k_pack_ranges(int64_t I_host, const uint32_t* __restrict__ I_dev, int64_t cap, const KeyT* __restrict__ keys,
-              const uint32_t* __restrict__ vals, const float4* __restrict__ rec_in, float4* __restrict__ rec_out,
-              uint2* __restrict__ ranges) {
+k_bin_prefix(int nchunks, int T, uint32_t* __restrict__ cnt, uint32_t* __restrict__ totals) {
+    __shared__ uint32_t part[8][32];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int t = blockIdx.x * 32 + lane;
+    const int per = (nchunks + 7) / 8;
+    const int c0 = slice * per, c1 = min(nchunks, c0 + per);
+    uint32_t s = 0;
+    if (t < T) {
+        const uint32_t* p = cnt + (size_t)c0 * T + t;
+#pragma unroll 8
+        for (int c = c0; c < c1; ++c, p += T) s += *p;
+    }
+    part[slice][lane] = s;
+    __syncthreads();
+    uint32_t run = 0;
+    for (int k = 0; k < slice; ++k) run += part[k][lane];
+    if (t < T) {
+        if (slice == 7) totals[t] = run + s;
+        uint32_t* p = cnt + (size_t)c0 * T + t;
+#pragma unroll 4
+        for (int c = c0; c < c1; ++c, p += T) { const uint32_t v = *p; *p = run; run += v; }
+    }
+}
+
+// ---- 2b. tile starts: exclusive scan of the column totals -> ranges, and the instance count.  One CTA.
+// count_out[0] = num_rendered (low 32 bits), count_out[1] = 1 if it does not fit 32 bits.
+__global__ void __launch_bounds__(1024)
+k_bin_ranges(int T, const uint32_t* __restrict__ totals, uint2* __restrict__ ranges, uint32_t* __restrict__ count_out) {
+    __shared__ unsigned long long warp_excl[32];
+    __shared__ unsigned long long block_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long carry = 0;                      // running total of the tiles in front (same in every thread)
+    for (int base = 0; base < T; base += 1024) {
+        const int t = base + threadIdx.x;
+        const unsigned long long v = t < T ? totals[t] : 0u;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long n = __shfl_up_sync(kFull, inc, o);
+            if (lane >= o) inc += n;
+        }
+        if (lane == 31) warp_excl[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned long long w = warp_excl[lane];
+            unsigned long long wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long n = __shfl_up_sync(kFull, wi, o);
+                if (lane >= o) wi += n;
+            }
+            warp_excl[lane] = wi - w;
+            if (lane == 31) block_total = wi;
+        }
+        __syncthreads();
+        const unsigned long long start = carry + warp_excl[warp] + (inc - v);
+        if (t < T) {
+            const unsigned long long end = start + v;
+            ranges[t] = v == 0 ? make_uint2(0u, 0u)          // untouched tiles = (0,0)
+                               : make_uint2((uint32_t)(start > 0xFFFFFFFFull ? 0xFFFFFFFFull : start),
+                                            (uint32_t)(end > 0xFFFFFFFFull ? 0xFFFFFFFFull : end));
+        }
+        carry += block_total;
+        __syncthreads();                               // warp_excl / block_total are rewritten by the next round
+    }
+    if (threadIdx.x == 0) {
+        count_out[0] = (uint32_t)(carry > 0xFFFFFFFFull ? 0xFFFFFFFFull : carry);
+        count_out[1] = carry > 0xFFFFFFFFull ? 1u : 0u;
+    }
+}
+
+// ---- 3. ordered scatter.  One single-warp CTA per (chunk, band); dynamic shared memory = the band's cursors + the
+// chunk's hit list.  The walk over the chunk's Gaussians is sequential by construction (order inside a tile = order
+// of the walk), so everything around it is organised to keep the walk short: phase 1 finds the Gaussians of the chunk
+// that touch the band (coalesced loads of the depth-ordered rectangles, ordered compaction by ballot), phase 2 walks
+// only those, 32 staged at a time in shared memory (one broadcast LDS.128 per Gaussian instead of shuffles).  The
+// tiles of one rectangle are distinct, so the lanes bump the cursors with plain LDS / STS (no atomics); __syncwarp
+// orders one Gaussian's bumps before the next one's.
+struct __align__(16) Staged { uint32_t base, w, magic, area; };   // base = (y0 - r0) * Tx + x0
+__global__ void __launch_bounds__(32)
+k_bin_scatter(int N, int chunk, const uint32_t* __restrict__ order, const uint2* __restrict__ span_sorted, int Tx, int Ty,
+              int rows_per_band, int T, const uint32_t* __restrict__ cnt, const uint2* __restrict__ ranges, uint32_t cap,
+              uint32_t* __restrict__ vals) {
+    extern __shared__ __align__(16) uint32_t smem_u32[];
+    __shared__ Staged stage[32];
+    __shared__ uint32_t stage_id[32];
+    uint32_t* cursor = smem_u32;                       // [band tiles]
+    const int lane = threadIdx.x;
+    const int band = blockIdx.y;
+    const int r0 = band * rows_per_band, r1 = min(Ty, r0 + rows_per_band);
+    const int nt = (r1 - r0) * Tx;
+    uint16_t* hits = reinterpret_cast<uint16_t*>(cursor + rows_per_band * Tx);   // [chunk]
+    {   // cursor[t] = start of tile t + instances of the chunks in front of this one
+        const uint32_t* row = cnt + (size_t)blockIdx.x * T + (size_t)r0 * Tx;
+        const uint2* rg = ranges + (size_t)r0 * Tx;
+#pragma unroll 4
+        for (int t = lane; t < nt; t += 32) cursor[t] = rg[t].x + row[t];
+    }
+    const int first = blockIdx.x * chunk, last = min(N, first + chunk);
+    // ---- phase 1 (throughput): which Gaussians of the chunk touch this band?  Ordered compaction by ballot.
+    int nh = 0;
+    for (int base = first; base < last; base += 128) {
+        uint32_t ys[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                  // four independent coalesced loads in flight
+            const int r = base + 32 * k + lane;
+            ys[k] = r < last ? span_sorted[r].y : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int y0 = (int)(ys[k] & 0xFFFF), y1 = (int)(ys[k] >> 16);
+            const bool hit = max(y0, r0) < min(y1, r1);
+            const unsigned m = __ballot_sync(kFull, hit);
+            if (hit) hits[nh + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(base - first + 32 * k + lane);
+            nh += __popc(m);
+        }
+    }
+    __syncwarp();
+    // ---- phase 2 (latency): walk the hits IN ORDER
+    for (int hb = 0; hb < nh; hb += 32) {
+        const int e = hb + lane;
+        const int n = min(32, nh - hb);
+        if (e < nh) {
+            const int r = first + (int)hits[e];
+            const RectClip c = clip_rect(span_sorted[r], r0, r1);
+            Staged sg;
+            sg.base = (c.y0 - (uint32_t)r0) * (uint32_t)Tx + c.x0; sg.w = c.w; sg.magic = magic_of(c.w); sg.area = c.w * c.h;
+            stage[lane] = sg;
+            stage_id[lane] = order[r];
+        }
+        __syncwarp();
+        for (int k = 0; k < n; ++k) {
+            const Staged q = stage[k];
+            const uint32_t gid = stage_id[k];
+            for (uint32_t l = lane; l < q.area; l += 32) {       // one round for rectangles of up to 32 tiles
+                uint32_t xx; const uint32_t yy = div_by(l, q.w, q.magic, xx);
+                const uint32_t t = q.base + yy * (uint32_t)Tx + xx;
+                const uint32_t pos = cursor[t];
+                cursor[t] = pos + 1;
+                if (pos < cap) vals[pos] = gid;                  // speculative mode: never write past the hint
+            }
+            __syncwarp();                                        // the next Gaussian's bumps come after this one's
+        }
+    }
+}
+
+// ---- 4. record packing.  256 instances per CTA: each thread gathers its instance's 48-byte record (3 x LDG.128;
+// the per-Gaussian record table is 48 MB at 1M splats and is kept L2-resident by evict_last loads while the
+// packed output streams through with an evict_first bulk store) into shared memory, and one thread writes the 12 KB
+// block back with a single TMA bulk store.
+__global__ void __launch_bounds__(256)
+k_pack(int64_t I_host, const uint32_t* __restrict__ I_dev, int64_t cap, const uint32_t* __restrict__ vals,
+       const float4* __restrict__ rec_in, float4* __restrict__ rec_out) {
     __shared__ __align__(128) float4 sm[256 * 3];
-    // exact mode: I_host; speculative mode: the real count lives on the device (last scan element), clamped
-    // to the buffer capacity (an overflowing speculation is discarded and re-run by the host)
+    // exact mode: I_host; speculative mode: the real count lives on the device, clamped to the buffer capacity
+    // (an overflowing speculation is discarded and re-run by the host)
     int64_t I = I_host;
     if (I_dev) { I = (int64_t)*I_dev; if (I > cap) I = cap; }
     const int64_t j0 = (int64_t)blockIdx.x * 256;
     if (j0 >= I) return;
     const int64_t j = j0 + threadIdx.x;
     if (j < I) {
-        const uint32_t id = vals[j];
+        uint32_t id;
+        asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(id) : "l"(vals + j));        // streamed once
         const float4* src = rec_in + (size_t)3 * id;
-        const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+        float4 a, b, c;
+        uint64_t keep;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+        asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(src), "l"(keep));
+        asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(src + 1), "l"(keep));
+        asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w) : "l"(src + 2), "l"(keep));
         sm[3 * threadIdx.x] = a; sm[3 * threadIdx.x + 1] = b; sm[3 * threadIdx.x + 2] = c;
-        const uint32_t tile = (uint32_t)keys[j];
-        if (j == 0) ranges[tile].x = 0;
-        else {
-            const uint32_t prev = (uint32_t)keys[j - 1];
-            if (prev != tile) { ranges[prev].y = (uint32_t)j; ranges[tile].x = (uint32_t)j; }
-        }
-        if (j == I - 1) ranges[tile].y = (uint32_t)I;
     }
     // make the generic-proxy shared-memory writes visible to the async proxy, then bulk-store
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -114,45 +334,14 @@ k_pack_ranges(int64_t I_host, const uint32_t* __restrict__ I_dev, int64_t cap, c
     if (threadIdx.x == 0) {
         const int64_t n = (I - j0) < 256 ? (I - j0) : 256;
         const uint32_t bytes = (uint32_t)n * 48u;
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(rec_out + 3 * j0),
-                     "r"((uint32_t)__cvta_generic_to_shared(sm)), "r"(bytes)
+        uint64_t policy;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(rec_out + 3 * j0),
+                     "r"((uint32_t)__cvta_generic_to_shared(sm)), "r"(bytes), "l"(policy)
                      : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released after the read
     }
-}
-
-template <typename KeyT>
-int emit_sort_pack(GeomView gv, BinView bv, int N, int64_t I, int64_t cap, bool spec, int T, int Tx, int tile_bits,
-                   cudaStream_t st) {
-    KeyT* ku = reinterpret_cast<KeyT*>(bv.tile_unsorted);
-    KeyT* ks = reinterpret_cast<KeyT*>(bv.tile_sorted);
-    {
-        TgsProfScope prof(TGS_STAGE_DUPLICATE, st);
-        // speculative mode sorts `cap` slots: the unused tail must sort behind every real tile id
-        if (spec) TGS_CUDA(cudaMemsetAsync(ku, 0xFF, sizeof(KeyT) * (size_t)cap, st));
-        k_emit<KeyT><<<(N + 255) / 256, 256, 0, st>>>(N, gv.order, gv.tiles_touched, gv.offsets, gv.rect, Tx,
-                                                      (uint32_t)(cap > 0xFFFFFFFFll ? 0xFFFFFFFFll : cap), ku,
-                                                      bv.vals_unsorted);
-        tgs_count_own(1);
-        TGS_CUDA(cudaGetLastError());
-    }
-    {
-        TgsProfScope prof(TGS_STAGE_SORT, st);
-        size_t bytes = bv.cub_temp_bytes;
-        TGS_CUDA(cub::DeviceRadixSort::SortPairs(bv.cub_temp, bytes, ku, ks, bv.vals_unsorted, bv.vals_sorted, I, 0,
-                                                 tile_bits, st));
-        tgs_count_cub(1);
-    }
-    {
-        TgsProfScope prof(TGS_STAGE_PACK, st);
-        k_pack_ranges<KeyT><<<(unsigned)((I + 255) / 256), 256, 0, st>>>(
-            I, spec ? gv.offsets + (N - 1) : nullptr, cap, ks, bv.vals_sorted,
-            reinterpret_cast<const float4*>(gv.records), reinterpret_cast<float4*>(bv.records), bv.ranges);
-        tgs_count_own(1);
-        TGS_CUDA(cudaGetLastError());
-    }
-    return 0;
 }
 
 }  // namespace
@@ -161,44 +350,85 @@ size_t tgs_depth_sort_temp_bytes(int N) {
     size_t a = 0, b = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
                                     (uint32_t*)nullptr, N, 0, 32);
-    TilesInOrder f{nullptr, nullptr};
-    TilesIt it(cub::CountingInputIterator<uint32_t>(0), f);
-    cub::DeviceScan::InclusiveSum(nullptr, b, it, (uint32_t*)nullptr, N);
+    cub::DeviceScan::InclusiveSum(nullptr, b, (const uint32_t*)nullptr, (uint32_t*)nullptr, N);   // refstructure arm
     return a > b ? a : b;
 }
 
-size_t tgs_tile_sort_temp_bytes(int64_t I, int T) {
-    size_t bytes = 0;
-    if (T < 65535)
-        cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint16_t*)nullptr, (uint16_t*)nullptr,
-                                        (const uint32_t*)nullptr, (uint32_t*)nullptr, I, 0, 16);
-    else
-        cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
-                                        (const uint32_t*)nullptr, (uint32_t*)nullptr, I, 0, 32);
-    return bytes;
+size_t tgs_bin_temp_bytes(int N, int Tx, int Ty) {
+    const Plan p = make_plan(N, Tx, Ty);
+    const size_t T = (size_t)Tx * Ty;
+    return tgs_align_up((size_t)p.nchunks * T * sizeof(uint32_t)) + tgs_align_up(T * sizeof(uint32_t));
 }
 
-// Phase 1 + scan: depth order of the Gaussians and the inclusive scan of tiles_touched in that order.
-int tgs_depth_order_and_scan(GeomView gv, int N, cudaStream_t st) {
+// Phase 0: depth order of the Gaussians.
+int tgs_depth_order(GeomView gv, int N, cudaStream_t st) {
     TgsProfScope prof(TGS_STAGE_SCAN, st);
     size_t bytes = gv.temp_bytes;
     TGS_CUDA(cub::DeviceRadixSort::SortPairs(gv.temp, bytes, gv.depth_keys, gv.depth_keys_sorted, gv.ids, gv.order, N,
                                              0, 32, st));
-    TilesInOrder f{gv.tiles_touched, gv.order};
-    TilesIt it(cub::CountingInputIterator<uint32_t>(0), f);
-    bytes = gv.temp_bytes;
-    TGS_CUDA(cub::DeviceScan::InclusiveSum(gv.temp, bytes, it, gv.offsets, N, st));
-    tgs_count_cub(2);
+    tgs_count_cub(1);
     return 0;
 }
 
-int tgs_emit_sort_pack(GeomView gv, BinView bv, int N, int64_t count, int64_t cap, bool speculative, int T, int Tx,
-                       cudaStream_t st) {
-    TGS_CUDA(cudaMemsetAsync(bv.ranges, 0, sizeof(uint2) * (size_t)T, st));
+// Phases 1-2: count matrix, per-tile prefixes, tile ranges and the instance count (on the device: count_out[0..1]).
+int tgs_bin_count(GeomView gv, int N, int Tx, int Ty, void* temp, uint2* ranges, uint32_t* count_out, cudaStream_t st) {
+    const int T = Tx * Ty;
+    if (N == 0) {
+        TGS_CUDA(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)T, st));
+        TGS_CUDA(cudaMemsetAsync(count_out, 0, 2 * sizeof(uint32_t), st));
+        return 0;
+    }
+    const Plan p = make_plan(N, Tx, Ty);
+    uint32_t* cnt = (uint32_t*)temp;
+    uint32_t* totals = (uint32_t*)((char*)temp + tgs_align_up((size_t)p.nchunks * T * sizeof(uint32_t)));
+    static bool attr_done[64] = {};
+    int dev = 0;
+    TGS_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_done[dev]) {
+        TGS_CUDA(cudaFuncSetAttribute(k_bin_count, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (TGS_BIN_BAND_TILES + 1) * 4));
+        TGS_CUDA(cudaFuncSetAttribute(k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, TGS_BIN_BAND_TILES * 4 + 8192 * 2));   // one row of a very wide image + the hit list
+        attr_done[dev] = true;
+    }
+    {
+        TgsProfScope prof(TGS_STAGE_DUPLICATE, st);
+        k_bin_count<<<dim3(p.nchunks, p.count.n), 256, (size_t)p.count.tiles * 4, st>>>(
+            N, p.chunk, gv.order, gv.tiles_touched, gv.rect, Tx, Ty, p.count.rows, T, cnt, gv.span_sorted);
+        tgs_count_own(1);
+        TGS_CUDA(cudaGetLastError());
+    }
+    {
+        TgsProfScope prof(TGS_STAGE_SORT, st);
+        k_bin_prefix<<<(T + 31) / 32, 256, 0, st>>>(p.nchunks, T, cnt, totals);
+        k_bin_ranges<<<1, 1024, 0, st>>>(T, totals, ranges, count_out);
+        tgs_count_own(2);
+        TGS_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+// Phases 3-4.  `cap` = instances the binning buffer holds; `count` = instances to pack (== I in exact mode, == cap in
+// speculative mode, where the real count is read on the device from count_dev).
+int tgs_bin_scatter_pack(GeomView gv, BinView bv, int N, int64_t count, int64_t cap, bool speculative, int Tx, int Ty,
+                         const void* temp, const uint2* ranges, const uint32_t* count_dev, cudaStream_t st) {
     if (count == 0 || N == 0) return 0;
-    int bits = 1;
-    while ((1 << bits) < T) ++bits;
-    if (speculative && (1 << bits) == T) ++bits;     // the all-ones pad key must compare above every tile id
-    if (T < 65535) return emit_sort_pack<uint16_t>(gv, bv, N, count, cap, speculative, T, Tx, bits, st);
-    return emit_sort_pack<uint32_t>(gv, bv, N, count, cap, speculative, T, Tx, bits > 32 ? 32 : bits, st);
+    const int T = Tx * Ty;
+    const Plan p = make_plan(N, Tx, Ty);
+    const uint32_t* cnt = (const uint32_t*)temp;
+    {
+        TgsProfScope prof(TGS_STAGE_BIN_SCATTER, st);
+        k_bin_scatter<<<dim3(p.nchunks, p.scatter.n), 32, (size_t)p.scatter.tiles * 4 + (size_t)p.chunk * 2, st>>>(
+            N, p.chunk, gv.order, gv.span_sorted, Tx, Ty, p.scatter.rows, T, cnt, ranges,
+            (uint32_t)(cap > 0xFFFFFFFFll ? 0xFFFFFFFFll : cap), bv.vals_sorted);
+        tgs_count_own(1);
+        TGS_CUDA(cudaGetLastError());
+    }
+    {
+        TgsProfScope prof(TGS_STAGE_PACK, st);
+        k_pack<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(
+            count, speculative ? count_dev : nullptr, cap, bv.vals_sorted, reinterpret_cast<const float4*>(gv.records),
+            reinterpret_cast<float4*>(bv.records));
+        tgs_count_own(1);
+        TGS_CUDA(cudaGetLastError());
+    }
+    return 0;
 }

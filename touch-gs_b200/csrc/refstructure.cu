@@ -257,12 +257,13 @@ extern "C" int tgs_refstructure_forward(const TgsSettings* s, const TgsGaussians
     GeomView gv = tgs_geom_view(geom, N);
     ImageView iv = tgs_image_view(image, cam.W, cam.H);
     int rc = tgs_launch_preprocess(cam, s, g, gv, radii, st); if (rc) return rc;
-    // scan in id order needs a place before the binning buffer exists: the geometry buffer's offsets array
+    // scan in id order needs a place before the binning buffer exists: the geometry buffer's `order` array (this arm
+    // does not depth-sort the Gaussians, so it is free)
     size_t tb = gv.temp_bytes;
-    TGS_CUDA(cub::DeviceScan::InclusiveSum(gv.temp, tb, gv.tiles_touched, gv.offsets, N, st));
+    TGS_CUDA(cub::DeviceScan::InclusiveSum(gv.temp, tb, gv.tiles_touched, gv.order, N, st));
     tgs_count_cub(1);
     uint32_t h_I = 0;
-    TGS_CUDA(cudaMemcpyAsync(&h_I, gv.offsets + (N - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    TGS_CUDA(cudaMemcpyAsync(&h_I, gv.order + (N - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     TGS_CUDA(cudaStreamSynchronize(st));               // the blocking read of num_rendered
     const int64_t I = (int64_t)h_I;
     TgsRefBinningLayout bl; tgs_refstructure_binning_layout(N, I, T, &bl);
@@ -271,7 +272,7 @@ extern "C" int tgs_refstructure_forward(const TgsSettings* s, const TgsGaussians
     RefBinView bv = ref_bin_view(binning, N, I, T);
     TGS_CUDA(cudaMemsetAsync(bv.ranges, 0, sizeof(uint2) * (size_t)T, st));
     if (I > 0) {
-        k_ref_duplicate<<<(N + kBlk - 1) / kBlk, kBlk, 0, st>>>(N, gv.records, gv.tiles_touched, gv.offsets, gv.rect,
+        k_ref_duplicate<<<(N + kBlk - 1) / kBlk, kBlk, 0, st>>>(N, gv.records, gv.tiles_touched, gv.order, gv.rect,
                                                                 cam.Tx, bv.keys_unsorted, bv.vals_unsorted);
         tgs_count_own(1);
         TGS_CUDA(cudaGetLastError());

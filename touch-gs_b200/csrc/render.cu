@@ -127,7 +127,7 @@ __device__ __forceinline__ bool patch_may_touch(const float4 a, const float4 q, 
 
 // ------------------------------------------------------------------------------- forward
 __global__ void __launch_bounds__(256)
-k_render_fwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ recs, int W, int H, int Tx,
+k_render_fwd(const uint2* __restrict__ ranges, uint32_t cap, const TgsRecord* __restrict__ recs, int W, int H, int Tx,
              int row0, const float* __restrict__ bg, int normalize, float alpha_max, float* __restrict__ out_color,
              float* __restrict__ out_depth, float* __restrict__ out_alpha, float* __restrict__ final_T,
              uint32_t* __restrict__ n_contrib, float* __restrict__ depth_raw, float* __restrict__ color_acc,
@@ -139,7 +139,10 @@ k_render_fwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
     const int tid = threadIdx.x, lane = tid & 31;
     const int tile = blockIdx.x + row0 * Tx;
     const PixelMap pm = map_pixel(tile, Tx, W, H);
-    const uint2 rng = ranges[tile];
+    uint2 rng = ranges[tile];
+    // speculative sizing: the buffers hold `cap` instances; if the real count overflows them this launch's result is
+    // discarded (the host re-runs with the exact size), but it must stay inside the buffers
+    rng.x = min(rng.x, cap); rng.y = min(rng.y, cap);
     const int len = (int)(rng.y - rng.x);
     const int nb = (len + kBatch - 1) / kBatch;
     if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
@@ -539,14 +542,14 @@ int tgs_launch_touch_loss_value(const float* residual, const float* weight, int6
     return 0;
 }
 
-int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, BinView bv, ImageView iv,
+int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, BinView bv, ImageView iv, int64_t capacity,
                           float* out_color, float* out_depth, float* out_alpha,
                           const float* touch_target, float* residual_out, cudaStream_t st) {
     int nt = cam.Tx * (cam.row1 - cam.row0);
     if (nt <= 0) return 0;
     TgsProfScope prof(TGS_STAGE_RENDER_FWD, st);
     TGS_CUDA(cudaMemsetAsync(bv.work_counter, 0, 2 * sizeof(uint32_t), st));
-    k_render_fwd<<<nt, 256, 0, st>>>(bv.ranges, bv.records, cam.W, cam.H, cam.Tx, cam.row0, s->bg,
+    k_render_fwd<<<nt, 256, 0, st>>>(iv.ranges, (uint32_t)(capacity > 0xFFFFFFFFll ? 0xFFFFFFFFll : capacity), bv.records, cam.W, cam.H, cam.Tx, cam.row0, s->bg,
                                      s->depth_normalize, cam.alpha_max, out_color, out_depth, out_alpha, iv.final_T,
                                      iv.n_contrib, iv.depth_raw, iv.color_acc, bv.ckpt, bv.slot_tile, bv.ckpt_list,
                                      bv.work_counter + 1, touch_target, residual_out);
@@ -587,7 +590,7 @@ int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, BinView bv, I
     int64_t grid = (units + kBwdWarps - 1) / kBwdWarps;
     if (grid > (int64_t)cps * sms) grid = (int64_t)cps * sms;        // persistent: one resident wave
     TGS_CUDA(cudaMemsetAsync(bv.work_counter, 0, sizeof(uint32_t), st));
-    k_render_bwd<<<(unsigned)grid, kBwdThreads, 0, st>>>(bv.ranges, bv.records, cam.W, cam.H, cam.Tx, cam.row0, s->bg,
+    k_render_bwd<<<(unsigned)grid, kBwdThreads, 0, st>>>(iv.ranges, bv.records, cam.W, cam.H, cam.Tx, cam.row0, s->bg,
                                      s->depth_normalize, cam.alpha_max, iv.final_T, iv.n_contrib, iv.depth_raw,
                                      iv.color_acc, bv.ckpt, bv.slot_tile, bv.ckpt_list, bv.work_counter, 2 * nt, dL_dcolor,
                                      dL_ddepth, dL_dalpha, tt, tw, ts, tg, mode, tr0, tr1, residual, screen_grads);

@@ -145,7 +145,6 @@ extern "C" int tgs_rasterize_screen_forward(const TgsSettings* s, int32_t N, con
         tgs_set_error("tgs_rasterize_screen_forward: NULL per-Gaussian tensor"); return TGS_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
     const TgsCam cam = tgs_make_cam(s);
-    const int T = cam.Tx * cam.Ty;
     TgsGeomLayout gl; tgs_geom_layout(N, &gl);
     TgsImageLayout il; tgs_image_layout(cam.W, cam.H, &il);
     void* geom = alloc(user, TGS_BUF_GEOM, gl.total);
@@ -154,25 +153,32 @@ extern "C" int tgs_rasterize_screen_forward(const TgsSettings* s, int32_t N, con
     GeomView gv = tgs_geom_view(geom, N);
     ImageView iv = tgs_image_view(image, cam.W, cam.H);
     int64_t I = 0;
+    void* temp = nullptr;
     if (N > 0) {
         k_screen_records<<<(N + 255) / 256, 256, 0, st>>>(N, xys, depths, radii, conics, colors, opacities, pixel_offset, cam,
                                                           gv.records, gv.tiles_touched, gv.rect, gv.depth_keys, gv.ids);
         tgs_count_own(1);
         TGS_CUDA(cudaGetLastError());
-        int rc = tgs_depth_order_and_scan(gv, N, st); if (rc) return rc;
-        uint32_t h_I = 0;
-        TGS_CUDA(cudaMemcpyAsync(&h_I, gv.offsets + (N - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        TGS_CUDA(cudaStreamSynchronize(st));
-        I = (int64_t)h_I;
+        int rc = tgs_depth_order(gv, N, st); if (rc) return rc;
+        temp = alloc(user, TGS_BUF_TEMP, tgs_bin_temp_bytes(N, cam.Tx, cam.Ty));
+        if (!temp) { tgs_set_error("allocator returned NULL"); return TGS_ENOMEM; }
     }
-    TgsBinningLayout bl; tgs_binning_layout(I, T, &bl);
+    int rc = tgs_bin_count(gv, N, cam.Tx, cam.Ty, temp, iv.ranges, iv.count, st); if (rc) return rc;
+    if (N > 0) {
+        uint32_t h_I[2] = {0, 0};
+        TGS_CUDA(cudaMemcpyAsync(h_I, iv.count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        TGS_CUDA(cudaStreamSynchronize(st));
+        if (h_I[1]) { tgs_set_error("num_rendered does not fit 32 bits"); return TGS_EINVAL; }
+        I = (int64_t)h_I[0];
+    }
+    TgsBinningLayout bl; tgs_binning_layout(I, &bl);
     void* binning = alloc(user, TGS_BUF_BINNING, bl.total);
     if (!binning) { tgs_set_error("allocator returned NULL"); return TGS_ENOMEM; }
-    BinView bv = tgs_bin_view(binning, I, T);
-    int rc = tgs_emit_sort_pack(gv, bv, N, I, I, false, T, cam.Tx, st); if (rc) return rc;
+    BinView bv = tgs_bin_view(binning, I);
+    rc = tgs_bin_scatter_pack(gv, bv, N, I, I, false, cam.Tx, cam.Ty, temp, iv.ranges, iv.count, st); if (rc) return rc;
     TgsSettings s2 = *s;
     s2.depth_normalize = 0;
-    rc = tgs_launch_render_fwd(cam, &s2, bv, iv, out_color, out_depth, out_alpha, nullptr, nullptr, st); if (rc) return rc;
+    rc = tgs_launch_render_fwd(cam, &s2, bv, iv, I, out_color, out_depth, out_alpha, nullptr, nullptr, st); if (rc) return rc;
     saved->geom = geom; saved->binning = binning; saved->image = image; saved->num_rendered = I; saved->capacity = I;
     return 0;
 }
@@ -184,7 +190,7 @@ extern "C" int tgs_rasterize_screen_backward(const TgsSettings* s, int32_t N, co
         tgs_set_error("tgs_rasterize_screen_backward: bad arguments"); return TGS_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
     const TgsCam cam = tgs_make_cam(s);
-    BinView bv = tgs_bin_view(saved->binning, saved->capacity > 0 ? saved->capacity : saved->num_rendered, cam.Tx * cam.Ty);
+    BinView bv = tgs_bin_view(saved->binning, saved->capacity > 0 ? saved->capacity : saved->num_rendered);
     ImageView iv = tgs_image_view(saved->image, cam.W, cam.H);
     if (N > 0) TGS_CUDA(cudaMemsetAsync(screen_grads, 0, sizeof(float) * TGS_NGRAD * (size_t)N, st));
     TgsSettings s2 = *s;

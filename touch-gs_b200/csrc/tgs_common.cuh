@@ -51,21 +51,18 @@ struct GeomView {
     TgsRecord* records;      // [N]
     float* cov3D;            // [N,6]
     uint32_t* tiles_touched; // [N]
-    uint32_t* offsets;       // [N] inclusive scan
     uint8_t* clamped;        // [N] bit c = colour channel c clamped at 0
     uint2* rect;             // [N] (rminx | rmaxx<<16, rminy | rmaxy<<16)
     uint32_t* depth_keys;    // [N] bits(depth) or 0xFFFFFFFF
     uint32_t* ids;           // [N] iota
     uint32_t* depth_keys_sorted;
     uint32_t* order;         // [N] ids in (depth, id) order
+    uint2* span_sorted;      // [N] rect of the Gaussians in that order
     void* temp; size_t temp_bytes;
 };
 struct BinView {
-    void* tile_unsorted; uint32_t* vals_unsorted;   // tile ids are uint16 when T <= 65536, else uint32
-    void* tile_sorted;   uint32_t* vals_sorted;
-    uint2* ranges;           // [T]
+    uint32_t* vals_sorted;   // [I] Gaussian ids in final (tile, depth, id) order
     TgsRecord* records;      // [I] packed, sorted
-    void* cub_temp; size_t cub_temp_bytes;
     float* ckpt;             // [slots][5][256] forward checkpoints at 256-record boundaries of the tile lists
     uint32_t* slot_tile;     // [slots] owning tile of the boundary in a slot (valid for the slots in ckpt_list)
     uint32_t* ckpt_list;     // [slots] slots the forward checkpointed, in completion order
@@ -75,12 +72,16 @@ struct BinView {
 struct ImageView {
     float* final_T; uint32_t* n_contrib; float* depth_raw;
     float* color_acc;        // [3][H*W] composited colour without the background term
+    uint2* ranges;           // [T] per-tile [start, end) into the sorted instance list
+    uint32_t* count;         // [2] num_rendered (device copy), overflow flag
 };
+#define TGS_BIN_BAND_TILES 8192     /* tiles per band of the count kernel: 32 KB of shared-memory counters */
+#define TGS_BIN_SCATTER_TILES 1024  /* tiles per band of the ordered scatter (one warp per (chunk, band)) */
 GeomView tgs_geom_view(void* base, int N);
-BinView tgs_bin_view(void* base, int64_t I, int T);
+BinView tgs_bin_view(void* base, int64_t I);
 ImageView tgs_image_view(void* base, int W, int H);
-size_t tgs_tile_sort_temp_bytes(int64_t I, int T);
 size_t tgs_depth_sort_temp_bytes(int N);
+size_t tgs_bin_temp_bytes(int N, int Tx, int Ty);
 
 // ------------------------------------------------------------------------ kernel launchers
 // preprocess.cu
@@ -93,13 +94,15 @@ int tgs_launch_preprocess_bwd(const TgsCam& cam, const TgsSettings* s, const Tgs
                               const TgsGrads* grads, cudaStream_t st);
 int tgs_launch_mark_visible(int N, const float* means, const float* vm, uint8_t* present, cudaStream_t st);
 // binning.cu
-int tgs_depth_order_and_scan(GeomView gv, int N, cudaStream_t st);
-// `cap` = instances the binning buffer holds; `count` = instances to sort (== I in exact mode, == cap in
-// speculative mode, where the real count is read on the device from gv.offsets[N-1])
-int tgs_emit_sort_pack(GeomView gv, BinView bv, int N, int64_t count, int64_t cap, bool speculative, int T, int Tx,
-                       cudaStream_t st);
+int tgs_depth_order(GeomView gv, int N, cudaStream_t st);
+// count matrix + per-tile prefixes + ranges + instance count (device: count_out[0] = I, count_out[1] = overflow flag)
+int tgs_bin_count(GeomView gv, int N, int Tx, int Ty, void* temp, uint2* ranges, uint32_t* count_out, cudaStream_t st);
+// `cap` = instances the binning buffer holds; `count` = instances to pack (== I in exact mode, == cap in speculative
+// mode, where the real count is read on the device from count_dev)
+int tgs_bin_scatter_pack(GeomView gv, BinView bv, int N, int64_t count, int64_t cap, bool speculative, int Tx, int Ty,
+                         const void* temp, const uint2* ranges, const uint32_t* count_dev, cudaStream_t st);
 // render.cu
-int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, BinView bv, ImageView iv,
+int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, BinView bv, ImageView iv, int64_t capacity,
                           float* out_color, float* out_depth, float* out_alpha,
                           const float* touch_target, float* residual_out, cudaStream_t st);
 int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, BinView bv, ImageView iv, int64_t num_rendered,

@@ -50,7 +50,45 @@ k_fuse_touch_vision(int64_t n, const unsigned short* __restrict__ touch, const u
     }
 }
 
+// Trainer-side decode of the on-disk maps (reference legacy/dataparser_tactile.py:65-66: depth_unit_scale_factor 1e-3;
+// :229-235: the pose scale factor also scales the depths): target = mm * unit, weight = f(sigma) with sigma = mm * 1e-3
+// (the uncertainty PNG is sigma x 1000, reference utils/fuse_touch_vision.py:376,387; sigma is NOT scaled with the scene).
+//   weight_mode 0: 1            (SIMPLE_LOSS)
+//   weight_mode 1: 1 / (uw * sigma)       weight_mode 2: 1 / (uw * sigma)^2       (0 where sigma == 0)
+__global__ void __launch_bounds__(256)
+k_decode_touch_maps(int64_t n, const unsigned short* __restrict__ depth_mm, const unsigned short* __restrict__ sigma_mm,
+                    float unit, float uw, int mode, float* __restrict__ target, float* __restrict__ weight) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (target) target[i] = (float)depth_mm[i] * unit;
+        if (weight) {
+            float w = 1.0f;
+            if (mode != 0 && sigma_mm) {
+                const float sg = (float)sigma_mm[i] * 1e-3f * uw;
+                w = sg > 0.0f ? (mode == 1 ? 1.0f / sg : 1.0f / (sg * sg)) : 0.0f;
+            }
+            weight[i] = w;
+        }
+    }
+}
+
 }  // namespace
+
+extern "C" int tgs_decode_touch_maps(const uint16_t* depth_mm, const uint16_t* sigma_mm, int64_t num_pixels,
+                                     float depth_unit, float uncertainty_weight, int32_t weight_mode, float* target,
+                                     float* weight, void* stream) {
+    if (num_pixels < 0 || weight_mode < 0 || weight_mode > 2 || (num_pixels > 0 && !depth_mm && target) ||
+        (num_pixels > 0 && weight && weight_mode != 0 && !sigma_mm) || !(uncertainty_weight > 0.0f)) {
+        tgs_set_error("tgs_decode_touch_maps: bad arguments"); return TGS_EINVAL; }
+    if (num_pixels == 0) return 0;
+    int64_t blocks = (num_pixels + 256 * 4 - 1) / (256 * 4);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_decode_touch_maps<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(num_pixels, depth_mm, sigma_mm, depth_unit,
+                                                                             uncertainty_weight, weight_mode, target, weight);
+    tgs_count_own(1);
+    TGS_CUDA(cudaGetLastError());
+    return 0;
+}
 
 extern "C" int tgs_fuse_touch_vision(const uint16_t* touch_mm, const uint16_t* vision_mm, const uint16_t* touch_sigma_mm,
                                      int64_t num_pixels, double scale, double offset, double offset2,

@@ -20,12 +20,6 @@ def _view(buf: torch.Tensor, off: int, count: int, dtype: torch.dtype) -> torch.
     return buf[off:off + nbytes].view(dtype)
 
 
-def _tiles(buf, off, count, key_bytes):
-    if key_bytes == 2:
-        return (_view(buf, off, count, torch.int16).to(torch.int64)) & 0xFFFF
-    return (_view(buf, off, count, torch.int32).to(torch.int64)) & 0xFFFFFFFF
-
-
 def forward_state(means3D, opacities, rs: GaussianRasterizationSettings, shs=None, colors_precomp=None,
                   scales=None, rotations=None, cov3D_precomp=None, opt: TouchOptions = None) -> Dict[str, torch.Tensor]:
     """Run the operator's forward (no grad) and return outputs + decoded internal state."""
@@ -52,7 +46,7 @@ def forward_state(means3D, opacities, rs: GaussianRasterizationSettings, shs=Non
     Tx, Ty = (W + TILE - 1) // TILE, (H + TILE - 1) // TILE
     gl, bl, il = L.TgsGeomLayout(), L.TgsBinningLayout(), L.TgsImageLayout()
     lib.tgs_geom_layout(N, C.byref(gl))
-    lib.tgs_binning_layout(cap, Tx * Ty, C.byref(bl))
+    lib.tgs_binning_layout(cap, C.byref(bl))
     lib.tgs_image_layout(W, H, C.byref(il))
     rec = _view(geom, gl.records, N * 12, torch.float32).view(N, 12)
     rect = _view(geom, gl.rect, N * 2, torch.int32).view(N, 2)
@@ -62,21 +56,31 @@ def forward_state(means3D, opacities, rs: GaussianRasterizationSettings, shs=Non
         conic=rec[:, 4:7], opacity=rec[:, 7], rgb=rec[:, 8:11],
         cov3D=_view(geom, gl.cov3D, N * 6, torch.float32).view(N, 6),
         tiles_touched=_view(geom, gl.tiles_touched, N, torch.int32),
-        offsets=_view(geom, gl.offsets, N, torch.int32),
         clamped=_view(geom, gl.clamped, N, torch.uint8),
         rect_min=torch.stack([rect[:, 0] & 0xFFFF, rect[:, 1] & 0xFFFF], -1),
         rect_max=torch.stack([(rect[:, 0] >> 16) & 0xFFFF, (rect[:, 1] >> 16) & 0xFFFF], -1),
         order=_view(geom, gl.order, N, torch.int32),
-        tile_ids=_tiles(binning, bl.tile_sorted, I, bl.key_bytes),
-        tile_ids_emitted=_tiles(binning, bl.tile_unsorted, I, bl.key_bytes),
-        vals_emitted=_view(binning, bl.vals_unsorted, I, torch.int32),
         vals=_view(binning, bl.vals_sorted, I, torch.int32),
-        ranges=_view(binning, bl.ranges, Tx * Ty * 2, torch.int32).view(Tx * Ty, 2),
+        ranges=_view(image, il.ranges, Tx * Ty * 2, torch.int32).view(Tx * Ty, 2),
+        num_rendered_device=int(_view(image, il.count, 2, torch.int32)[0].item()) & 0xFFFFFFFF,
         records=_view(binning, bl.records, I * 12, torch.float32).view(I, 12),
         final_T=_view(image, il.final_T, H * W, torch.float32).view(H, W),
         n_contrib=_view(image, il.n_contrib, H * W, torch.int32).view(H, W),
         depth_raw=_view(image, il.depth_raw, H * W, torch.float32).view(H, W),
     )
+    # The binning never materialises per-instance tile ids (binning.cu: positions come from counting rectangles):
+    # the tile of sorted position j is the tile whose [start, end) range holds j.
+    rg = out["ranges"].to(torch.int64) & 0xFFFFFFFF
+    lens = (rg[:, 1] - rg[:, 0]).clamp_min(0)
+    tile_of_range = torch.repeat_interleave(torch.arange(Tx * Ty, device=rg.device), lens)
+    tid = torch.full((I,), -1, dtype=torch.int64, device=rg.device)
+    if tile_of_range.numel() == I and I > 0:
+        # ranges tile the list without gaps or overlaps iff starts are the exclusive scan of the lengths
+        starts = torch.cumsum(lens, 0) - lens
+        ok = bool((rg[lens > 0, 0] == starts[lens > 0]).all())
+        if ok:
+            tid = tile_of_range
+    out["tile_ids"] = tid
     # the spec'd 64-bit sort key of every sorted instance: tile << 32 | bits(depth of its Gaussian)
     dbits = out["gdepth"].contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
     out["keys"] = (out["tile_ids"] << 32) | dbits[out["vals"].long()]
