@@ -388,17 +388,22 @@ def render_tiles(pre: Pre, bins: Bins, S: OracleSettings, tiles=None) -> Img:
     return Img(color, depth, 1.0 - fT, fT, ncon)
 
 
-def render_naive(pre: Pre, bins: Bins, S: OracleSettings) -> Img:
+def render_naive(pre: Pre, bins: Bins, S: OracleSettings, rows=None) -> Img:
     """The intentionally naive per-pixel / per-Gaussian Python loop (the "pure-PyTorch
-    rasterize_gaussians" CPU path of BASELINE config #1).  Differentiable; tiny sizes only."""
+    rasterize_gaussians" CPU path of BASELINE config #1).  Differentiable; tiny sizes only.
+    ``rows``: optional set of pixel rows to composite (the others stay at the background): bounded-sample timing."""
     dt = pre.xy.dtype
     W, H = S.image_width, S.image_height
     Tx = (W + TILE - 1) // TILE
     bg = S.bg.to(dt)
+    rows = None if rows is None else set(int(r) for r in rows)
     rows_c, rows_d, rows_t, rows_n = [], [], [], []
     for yy in range(H):
         rc, rd, rt, rn = [], [], [], []
         for xx in range(W):
+            if rows is not None and yy not in rows:
+                rc.append(bg.clone()); rd.append(torch.zeros((), dtype=dt)); rt.append(torch.ones((), dtype=dt)); rn.append(0)
+                continue
             t = (yy // TILE) * Tx + xx // TILE
             lo, hi = int(bins.ranges[t, 0]), int(bins.ranges[t, 1])
             T = torch.ones((), dtype=dt)
@@ -485,14 +490,14 @@ class OracleOut(NamedTuple):
 def rasterize(means3D, opacities, S: OracleSettings, shs=None, colors_precomp=None,
               scales=None, rotations=None, cov3D_precomp=None,
               touch_depth=None, touch_weight=None, depth_loss="none", depth_loss_mult=1.0,
-              depth_normalize=True, depth_loss_norm=None, band=None, naive=False) -> OracleOut:
+              depth_normalize=True, depth_loss_norm=None, band=None, naive=False, naive_rows=None) -> OracleOut:
     """Full forward of the operator on CPU.  Differentiable w.r.t. all float inputs.
 
     To compare with the CUDA operator's fused backward, backpropagate
     ``(g_rgb * out.color).sum() + out.touch_loss`` (+ any external depth/alpha terms)."""
     pre = preprocess(means3D, scales, rotations, opacities, shs, colors_precomp, cov3D_precomp, S, band)
     bins = bin_and_sort(pre, S)
-    img = render_naive(pre, bins, S) if naive else render_tiles(pre, bins, S)
+    img = render_naive(pre, bins, S, naive_rows) if naive else render_tiles(pre, bins, S)
     H, W = S.image_height, S.image_width
     if touch_depth is not None and depth_loss != "none":
         scale = loss_scale_from_target(touch_depth, depth_loss_mult, depth_loss_norm)

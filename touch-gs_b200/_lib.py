@@ -189,6 +189,53 @@ def load() -> C.CDLL:
     return lib
 
 
+_ext = None
+_ext_error = None
+
+
+def load_ext():
+    """The PyTorch C++ extension module `_C` (csrc/torch_ext.cpp -> _C.so next to libtgs.so): the operator's default
+    binding (TORCH_CHECK argument errors, at::empty allocations, current CUDA stream, CUDAGuard).  Returns None when
+    it has not been built; the caller then uses the ctypes binding of the same library (never a CPU path)."""
+    global _ext, _ext_error
+    if _ext is not None or _ext_error is not None:
+        return _ext
+    path = os.path.join(HERE, "_C.so")
+    if os.environ.get("TGS_BINDING", "").lower() == "ctypes" or not os.path.exists(path):
+        _ext_error = "disabled" if os.path.exists(path) else "not built"
+        return None
+    try:
+        load()                                   # libtgs.so first (the extension links against it)
+        import importlib.machinery
+        import importlib.util
+        import torch  # noqa: F401  (libtorch must be loaded before the extension)
+        loader = importlib.machinery.ExtensionFileLoader("touchgs_b200_C", path)
+        spec = importlib.util.spec_from_file_location("touchgs_b200_C", path, loader=loader)
+        mod = importlib.util.module_from_spec(spec)
+        loader.exec_module(mod)
+        if mod.abi_version() != TGS_ABI_VERSION:
+            raise ImportError(f"_C.so was built against ABI {mod.abi_version()}, expected {TGS_ABI_VERSION}; rebuild")
+        _ext = mod
+    except Exception as e:  # noqa: BLE001
+        import warnings
+        _ext_error = e
+        warnings.warn(f"touchgs_b200: the torch extension _C.so failed to load ({type(e).__name__}: {e}); "
+                      "using the ctypes binding of libtgs.so")
+    return _ext
+
+
+def use_binding(name: str) -> None:
+    """Select the operator's binding for subsequent calls: "ext" (the torch C++ extension, default when built) or
+    "ctypes".  For tests and the host-overhead measurement; both bindings drive the same kernels."""
+    global _ext, _ext_error
+    if name not in ("ext", "ctypes"):
+        raise ValueError("binding must be 'ext' or 'ctypes'")
+    os.environ["TGS_BINDING"] = "" if name == "ext" else "ctypes"
+    _ext, _ext_error = None, None
+    if name == "ext" and load_ext() is None:
+        raise ImportError(f"the torch extension is unavailable: {_ext_error}")
+
+
 def check(rc: int, what: str) -> None:
     if rc != 0:
         msg = load().tgs_last_error()

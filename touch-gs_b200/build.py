@@ -82,5 +82,39 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+EXT_SRC = os.path.join(CSRC, "torch_ext.cpp")
+EXT_OUT = os.path.join(HERE, "_C.so")
+
+
+def build_torch_ext(force: bool = False) -> str:
+    """g++ build of the PyTorch binding `_C` (csrc/torch_ext.cpp) against the installed torch and the in-tree
+    libtgs.so (found at run time through an $ORIGIN rpath).  No CUDA code lives here: nothing to compile with nvcc."""
+    import torch
+    from torch.utils import cpp_extension as ce
+    lib = build()
+    deps = [EXT_SRC, os.path.join(HERE, "..", "include", "tgs.h"), os.path.abspath(__file__), lib]
+    if not force and not _stale(deps, EXT_OUT):
+        return EXT_OUT
+    inc = []
+    for d in ce.include_paths(device_type="cuda") if "device_type" in ce.include_paths.__code__.co_varnames else ce.include_paths(cuda=True):
+        inc += ["-isystem", d]
+    import sysconfig
+    inc += ["-isystem", sysconfig.get_paths()["include"]]
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    abi = int(getattr(torch._C, "_GLIBCXX_USE_CXX11_ABI", 1))
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-DTORCH_EXTENSION_NAME=touchgs_b200_C",
+           "-DTORCH_API_INCLUDE_EXTENSION_H", f"-D_GLIBCXX_USE_CXX11_ABI={abi}", *inc, EXT_SRC, "-o", EXT_OUT,
+           f"-L{HERE}", "-l:libtgs.so", f"-L{tlib}", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch",
+           "-ltorch_python", "-L/usr/local/cuda/lib64", "-lcudart",
+           "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tlib}", "-Wl,-rpath,/usr/local/cuda/lib64"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    with open(os.path.join(OBJ, "torch_ext.log"), "w") as f:
+        f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError(f"g++ failed for torch_ext.cpp:\n{r.stdout[-3000:]}\n{r.stderr[-6000:]}")
+    return EXT_OUT
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_torch_ext(force="--force" in sys.argv))

@@ -63,9 +63,10 @@ Tensor f32(const Tensor& t, const char* name, std::vector<int64_t> shape, const 
         TORCH_CHECK(shape[i] < 0 || t.size(i) == shape[i], name, " must have shape ", at::IntArrayRef(shape), ", got ", t.sizes());
     return t.contiguous();
 }
-bool present(const Tensor& t) { return t.defined() && t.numel() > 0; }
-const float* fp(const Tensor& t) { return present(t) ? t.data_ptr<float>() : nullptr; }
-float* fpm(Tensor& t) { return present(t) ? t.data_ptr<float>() : nullptr; }
+// an absent optional tensor is passed as undefined or as the 1-D zero-element placeholder (the reference-era module's
+// torch.Tensor([])); a [0,K,3] tensor of an EMPTY scene is present
+bool present(const Tensor& t) { return t.defined() && !(t.dim() <= 1 && t.numel() == 0); }
+const float* fp(const Tensor& t) { return (t.defined() && t.numel() > 0) ? t.data_ptr<float>() : nullptr; }
 
 struct Inputs {           // validated, contiguous views + the C structs that point into them
     Tensor bg, means3D, colors, opacity, scales, rotations, cov3D, view, proj, sh, campos;
@@ -208,17 +209,13 @@ GradOut make_grads(const Inputs& in) {
     auto fo = at::TensorOptions().dtype(at::kFloat).device(in.means3D.device());
     GradOut o;
     o.dmeans2D = at::empty({N, 3}, fo); o.dmeans3D = at::empty({N, 3}, fo); o.dopacity = at::empty({N}, fo);
-    if (present(in.sh) || in.g.shs) o.dsh = at::empty({N, in.s.sh_coeffs, 3}, fo);
-    if (in.g.colors_precomp) o.dcolors = at::empty({N, 3}, fo);
-    if (in.g.scales) { o.dscales = at::empty({N, 3}, fo); o.drot = at::empty({N, 4}, fo); }
-    if (in.g.cov3D_precomp) o.dcov3D = at::empty({N, 6}, fo);
-    o.g.dmeans2D = o.dmeans2D.data_ptr<float>(); o.g.dmeans3D = o.dmeans3D.data_ptr<float>();
-    o.g.dopacity = o.dopacity.data_ptr<float>();
-    o.g.dshs = o.dsh.defined() ? o.dsh.data_ptr<float>() : nullptr;
-    o.g.dcolors = o.dcolors.defined() ? o.dcolors.data_ptr<float>() : nullptr;
-    o.g.dscales = o.dscales.defined() ? o.dscales.data_ptr<float>() : nullptr;
-    o.g.drotations = o.drot.defined() ? o.drot.data_ptr<float>() : nullptr;
-    o.g.dcov3D = o.dcov3D.defined() ? o.dcov3D.data_ptr<float>() : nullptr;
+    if (in.sh.defined()) o.dsh = at::empty({N, in.s.sh_coeffs, 3}, fo);
+    if (in.colors.defined()) o.dcolors = at::empty({N, 3}, fo);
+    if (in.scales.defined()) { o.dscales = at::empty({N, 3}, fo); o.drot = at::empty({N, 4}, fo); }
+    if (in.cov3D.defined()) o.dcov3D = at::empty({N, 6}, fo);
+    o.g.dmeans2D = (float*)fp(o.dmeans2D); o.g.dmeans3D = (float*)fp(o.dmeans3D); o.g.dopacity = (float*)fp(o.dopacity);
+    o.g.dshs = (float*)fp(o.dsh); o.g.dcolors = (float*)fp(o.dcolors); o.g.dscales = (float*)fp(o.dscales);
+    o.g.drotations = (float*)fp(o.drot); o.g.dcov3D = (float*)fp(o.dcov3D);
     return o;
 }
 using GradTuple = std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor>;

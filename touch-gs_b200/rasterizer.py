@@ -196,7 +196,142 @@ def _zero_scalar(device):
 
 
 def _empty_if(t):
-    return None if (t is None or t.numel() == 0) else t
+    """None for an absent optional tensor: None itself or the 1-D zero-element placeholder of the reference-era module
+    (``torch.Tensor([])``).  The [0,K,3] tensors of an EMPTY scene are present."""
+    return None if (t is None or (t.numel() == 0 and t.dim() <= 1)) else t
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Default binding: the PyTorch C++ extension `_C` (csrc/torch_ext.cpp): one call per direction, argument checking
+# (TORCH_CHECK), output / scratch allocation (at::empty), stream and device guard all happen in C++.
+def _forward_ext(ext, ctx, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, opt):
+    dev = means3D.device
+    e = _empty_on(dev)
+    sh, colors_precomp = _empty_if(sh), _empty_if(colors_precomp)
+    scales, rotations, cov3Ds_precomp = _empty_if(scales), _empty_if(rotations), _empty_if(cov3Ds_precomp)
+    H, W = int(rs.image_height), int(rs.image_width)
+    Ty = (H + TILE - 1) // TILE
+    r0, r1 = (0, Ty) if opt.tile_rows is None else (int(opt.tile_rows[0]), int(opt.tile_rows[1]))
+    if not (0 <= r0 <= r1 <= Ty):
+        raise ValueError(f"tile_rows {opt.tile_rows} outside [0, {Ty}]")
+    touch_depth, touch_weight = opt.touch_depth, opt.touch_weight
+    if opt.depth_loss != "none" and touch_depth is None:
+        raise ValueError("depth_loss != 'none' requires touch_depth")
+    if touch_weight is not None and touch_weight.numel() != H * W:
+        raise ValueError(f"touch_weight must have H*W = {H * W} elements, got {list(touch_weight.shape)}")
+    sh_ = e if sh is None else sh
+    col_ = e if colors_precomp is None else colors_precomp
+    sc_ = e if scales is None else scales
+    rot_ = e if rotations is None else rotations
+    cov_ = e if cov3Ds_precomp is None else cov3Ds_precomp
+    args = (rs.bg, means3D, col_, opacities, sc_, rot_, float(rs.scale_modifier), cov_, rs.viewmatrix, rs.projmatrix,
+            float(rs.tanfovx), float(rs.tanfovy), H, W, sh_, int(rs.sh_degree), rs.campos, bool(rs.prefiltered), bool(rs.debug),
+            r0, r1, bool(opt.depth_normalize), max(0, int(opt.rendered_hint or 0)), touch_depth)
+    try:
+        num_rendered, color, depth, alpha, radii, geom, binning, image, resid, capacity = ext.rasterize_gaussians(*args)
+    except Exception:
+        if rs.debug:
+            # reference-era operator habit (SURVEY §8b "Errors"): with debug=True a failing forward leaves its arguments
+            # behind for post-mortem inspection
+            try:
+                torch.save(dict(means3D=means3D, opacities=opacities, shs=sh, colors_precomp=colors_precomp, scales=scales,
+                                rotations=rotations, cov3D_precomp=cov3Ds_precomp, settings=tuple(rs)), "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+            except Exception:  # noqa: BLE001 - the dump is best effort; the real error is raised below
+                pass
+        raise
+    tscale, tloss = None, None
+    if touch_depth is not None and opt.depth_loss != "none":
+        norm = float(opt.depth_loss_norm) if opt.depth_loss_norm is not None else 0.0
+        tscale = ext.touch_loss_scale(touch_depth, float(opt.depth_loss_mult), norm)
+        if opt.return_touch_loss:
+            full = (r0 == 0 and r1 == Ty)
+            tr = (0, 0) if opt.touch_rows is None else (int(opt.touch_rows[0]), int(opt.touch_rows[1]))
+            if opt.touch_rows is None and not full:
+                tr = (min(r0 * TILE, H), min(r1 * TILE, H))
+            tloss = ext.touch_loss_value(resid, touch_weight, H, W, tr[0], tr[1], L.LOSS_MODES[opt.depth_loss], tscale)
+    ctx.ext = ext
+    ctx.rs, ctx.opt, ctx.rows = rs, opt, (r0, r1)
+    ctx.tscale = tscale
+    ctx.num_rendered, ctx.capacity = int(num_rendered), int(capacity)
+    ctx.opacity_shape = tuple(opacities.shape)
+    if opt.info is not None:
+        opt.info["num_rendered"] = ctx.num_rendered
+        opt.info["capacity"] = ctx.capacity
+    ctx.has = (sh is not None, colors_precomp is not None, scales is not None, cov3Ds_precomp is not None)
+    ctx.touch = (touch_depth, touch_weight)
+    ctx.save_for_backward(means3D, opacities, sh_, col_, sc_, rot_, cov_, radii, geom, binning, image)
+    ctx.set_materialize_grads(False)
+    if tloss is None:
+        tloss = _zero_scalar(dev)
+        ctx.mark_non_differentiable(radii, resid, tloss)
+    else:
+        ctx.mark_non_differentiable(radii, resid)
+    return color, radii, depth, alpha, resid, tloss
+
+
+def _backward_ext(ctx, g_color, g_depth, g_alpha, g_tloss):
+    ext = ctx.ext
+    (means3D, opacities, sh, colors, scales, rots, cov3D, radii, geom, binning, image) = ctx.saved_tensors
+    rs, opt = ctx.rs, ctx.opt
+    dev = means3D.device
+    N = int(means3D.shape[0])
+    H, W = int(rs.image_height), int(rs.image_width)
+    r0, r1 = ctx.rows
+    if g_color is None:
+        g_color = torch.zeros((3, H, W), dtype=torch.float32, device=dev)
+    touch_depth, touch_weight = ctx.touch
+    mode, gs = L.LOSS_NONE, None
+    if touch_depth is not None and opt.depth_loss != "none":
+        # upstream gradient of the touch-loss scalar, applied on the device (see the ctypes path for the semantics)
+        mode = L.LOSS_MODES[opt.depth_loss]
+        if opt.return_touch_loss:
+            if g_tloss is None:
+                mode = L.LOSS_NONE
+            else:
+                gs = g_tloss.detach().reshape(1).to(device=dev, dtype=torch.float32)
+        elif opt.loss_grad_scale is not None:
+            gs = torch.as_tensor(opt.loss_grad_scale, dtype=torch.float32, device=dev).detach().reshape(1)
+    tr = (0, 0) if opt.touch_rows is None else (int(opt.touch_rows[0]), int(opt.touch_rows[1]))
+    cam = (float(rs.scale_modifier), cov3D, rs.viewmatrix, rs.projmatrix, float(rs.tanfovx), float(rs.tanfovy))
+    peer = opt.peer_exchange if N > 0 else None
+    if peer is not None and N > peer.capacity:
+        if opt.process_group is None:
+            raise ValueError(f"PeerScreenGrads capacity {peer.capacity} < {N} Gaussians and no process_group to fall back to")
+        peer = None
+    if peer is None and opt.process_group is None:
+        # single GPU: RasterizeGaussiansBackwardCUDA in one call
+        grads = ext.rasterize_gaussians_backward(
+            rs.bg, means3D, radii, colors, opacities, scales, rots, *cam, g_color, g_depth, g_alpha, sh, int(rs.sh_degree),
+            rs.campos, geom, ctx.num_rendered, binning, image, ctx.capacity, bool(rs.debug), r0, r1, bool(opt.depth_normalize),
+            touch_depth if mode != L.LOSS_NONE else None, touch_weight, mode, ctx.tscale, gs, tr[0], tr[1])
+    else:
+        if peer is not None:
+            sgrad, peer_ptrs, peer_handle = peer.acquire(N)         # this rank's peer-mapped buffer of the step
+        else:
+            sgrad = torch.empty((max(N, 1), L.NGRAD), dtype=torch.float32, device=dev)
+        ext.backward_render(rs.bg, means3D, colors, opacities, scales, rots, *cam, H, W, sh, int(rs.sh_degree), rs.campos,
+                            bool(rs.debug), r0, r1, bool(opt.depth_normalize), geom, binning, image, ctx.num_rendered,
+                            ctx.capacity, g_color, g_depth, g_alpha, touch_depth if mode != L.LOSS_NONE else None, touch_weight,
+                            mode, ctx.tscale, gs, tr[0], tr[1], sgrad)
+        pre = (means3D, radii, colors, opacities, scales, rots, *cam, H, W, sh, int(rs.sh_degree), rs.campos, bool(rs.debug), geom)
+        if peer is not None:
+            # FUSED exchange (SURVEY §8e): wait until every rank has finished BACKWARD::render, then the chain-rule
+            # kernel gathers each Gaussian's partial sums straight from the owning peers' buffers over NVLink
+            peer_handle.barrier(channel=0)
+            grads = ext.backward_preprocess(*pre, None, [int(p or 0) for p in peer_ptrs], [int(v) for b in peer.bands for v in b])
+        else:
+            # the ONE exchange step of the multi-GPU path: sum the compact [N,10] screen-space gradients of all
+            # tile-row bands (SURVEY §8e), NCCL over NVLink
+            import torch.distributed as dist
+            dist.all_reduce(sgrad, op=dist.ReduceOp.SUM, group=opt.process_group)
+            grads = ext.backward_preprocess(*pre, sgrad, [], [])
+    dmeans2D, dcol, dopac, dmeans3D, dcov, dsh, dsc, drot = grads
+    has_sh, has_col, has_sr, has_cov = ctx.has
+    out = (dmeans3D, dmeans2D, dsh if has_sh else None, dcol if has_col else None, dopac.reshape(ctx.opacity_shape),
+           dsc if has_sr else None, drot if has_sr else None, dcov if has_cov else None)
+    need = ctx.needs_input_grad
+    return tuple(g if need[i] else None for i, g in enumerate(out)) + (None, None)
 
 
 class _RasterizeGaussians(torch.autograd.Function):
@@ -211,6 +346,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         dev = means3D.device
         if dev.type != "cuda":
             raise RuntimeError("touchgs_b200 rasterizer is CUDA-only (no CPU fallback); tensors are on " + str(dev))
+        ext = L.load_ext()
+        if ext is not None:
+            return _forward_ext(ext, ctx, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, opt)
         sh, colors_precomp = _empty_if(sh), _empty_if(colors_precomp)
         scales, rotations, cov3Ds_precomp = _empty_if(scales), _empty_if(rotations), _empty_if(cov3Ds_precomp)
         N = int(means3D.shape[0])
@@ -313,6 +451,8 @@ class _RasterizeGaussians(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_color, _g_radii, g_depth, g_alpha, _g_resid, g_tloss=None):
+        if getattr(ctx, "ext", None) is not None:
+            return _backward_ext(ctx, g_color, g_depth, g_alpha, g_tloss)
         lib = L.load()
         (means3D, opacities, sh, colors, scales, rots, cov3D, radii, geom, binning, image) = ctx.saved_tensors
         has_sh, has_col, has_sr, has_cov = ctx.has
@@ -432,6 +572,10 @@ class GaussianRasterizer(torch.nn.Module):
         dev = positions.device
         if dev.type != "cuda":
             raise RuntimeError("touchgs_b200 rasterizer is CUDA-only (no CPU fallback)")
+        ext = L.load_ext()
+        if ext is not None:
+            with torch.no_grad():
+                return ext.mark_visible(positions.detach(), rs.viewmatrix, rs.projmatrix)
         with torch.no_grad(), torch.cuda.device(dev):
             N = int(positions.shape[0])
             pos = _chk(positions.detach(), "positions", (N, 3), dev)
