@@ -60,6 +60,7 @@ def parse():
                     help="multi-GPU exchange of the [N,10] screen gradients: p2p = gather fused into the preprocess-backward "
                          "kernel over peer-mapped memory (NVLink); nccl = one all-reduce (also the fallback if p2p is unavailable)")
     ap.add_argument("--no-hints", action="store_true", help="synchronous sizing in every forward (no rendered_hint)")
+    ap.add_argument("--even-bands", action="store_true", help="N > 1: equal tile-row bands instead of bands balanced by instance count")
     ap.add_argument("--no-measured-configs", action="store_true",
                     help="--impl reference: skip the full CPU runs of configs c1 / c2 (about a minute on 8 cores)")
     return ap.parse_args()
@@ -596,6 +597,27 @@ def main():
     band = None if world == 1 else T.sharding.even_bands(H, world)[rank]
 
     scene, params, batches, bg = make_workload(cfg, N, args.cameras, dev, rank, band)
+    bands_all, band_policy = None, "single GPU"
+    if world > 1:
+        bands_all, band_policy = T.sharding.even_bands(H, world), "even tile rows"
+        if not args.even_bands:
+            # bands balanced by measured work (SURVEY §8e "balance by instance count, not rows"): instances per tile row,
+            # summed over the workload's cameras, from one untimed full-image forward per camera (identical on every rank)
+            row_work = torch.zeros(Ty, dtype=torch.float64)
+            with torch.no_grad():
+                for b in batches:
+                    d = b["dev"]
+                    rs0 = T.GaussianRasterizationSettings(H, W, b["cam"].tanfovx, b["cam"].tanfovy, bg, 1.0, d["view"], d["proj"],
+                                                          cfg["sh_degree"], d["campos"], False, False)
+                    st0 = T.inspect_state.forward_state(params["means3D"].detach(), params["opacities"].detach(), rs0,
+                                                        shs=params["shs"].detach(), scales=params["scales"].detach(),
+                                                        rotations=params["rotations"].detach())
+                    rg = st0["ranges"].long()
+                    row_work += (rg[:, 1] - rg[:, 0]).clamp_min(0).view(Ty, Tx).sum(1).double().cpu()
+                    del st0
+            bands_all = T.sharding.balanced_bands([float(v) + 1.0 for v in row_work], world)
+            band_policy = "balanced by instances per tile row (measured over the workload's cameras)"
+        band = tuple(bands_all[rank])
     train_mode = args.workload == "train_step"
     if train_mode:
         stepper = TrainStepper(cfg, params, bg, dev, band, group, args.refine_every)
@@ -613,7 +635,7 @@ def main():
         if args.exchange == "p2p":
             peer = T.sharding.make_peer_exchange(group, int(N * (3 if train_mode else 1)), dev)
             if peer is not None:
-                peer.bands = T.sharding.even_bands(H, world)
+                peer.bands = [tuple(b) for b in bands_all]
                 stepper.peer = peer
                 if train_mode:
                     stepper.trainer.peer = peer
@@ -824,6 +846,7 @@ def main():
                                f"(mult {DEPTH_LOSS_MULT}), {len(batches)} orbit cameras cycled",
                    "num_rendered_cam0": I_cam0, "visible_cam0": n_vis,
                    "parallelism": "single GPU" if world == 1 else f"tile-row shard x{world}; [N,10] fp32 screen-gradient exchange: {exchange}",
+                   "bands": None if bands_all is None else {"policy": band_policy, "tile_rows": [list(b) for b in bands_all]},
                    "rendered_hint": "off (synchronous sizing)" if args.no_hints else "per-view instance count of the previous visit +5% (speculative sizing; exact re-run on overflow)",
                    "l2_policy": "working set per step (params+grads 472 MB, instance records >250 MB) exceeds the 126 MB L2; no explicit flush"},
         "clocks": clocks,

@@ -108,8 +108,8 @@ def test_extension_and_ctypes_bindings_agree_and_host_overhead(ext):
         for a, b in zip(oe, oc):
             assert torch.equal(a, b), "forward outputs of the two bindings differ"
         for k in names:
-            assert rel_inf(ge[k], gc[k]) < 2e-6, k                 # same kernels; atomics reorder the sums
-        assert rel_inf(me, mc) < 2e-6
+            assert rel_inf(ge[k], gc[k]) < 1e-5, k                 # same kernels; atomics reorder the sums
+        assert rel_inf(me, mc) < 1e-5
         # host overhead of a (tiny, launch-bound) forward + backward through each binding
         run("ext", 20); run("ctypes", 20)
         te = min(run("ext", 200)[3] for _ in range(3))

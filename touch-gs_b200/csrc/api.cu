@@ -234,7 +234,7 @@ extern "C" int tgs_forward(const TgsSettings* s, const TgsGaussians* g, tgs_allo
         binning = alloc(user, TGS_BUF_BINNING, bl.total);
         if (!binning) { tgs_set_error("allocator returned NULL"); return TGS_ENOMEM; }
         BinView bv = tgs_bin_view(binning, capacity);
-        int r = tgs_bin_scatter_pack(gv, bv, N, count, capacity, spec, cam.Tx, cam.Ty, temp, iv.ranges, iv.count, st); if (r) return r;
+        int r = tgs_bin_scatter_pack(gv, bv, N, count, capacity, spec, cam.Tx, cam.Ty, cam.row0, cam.row1, temp, iv.ranges, iv.count, st); if (r) return r;
         if (s->debug) TGS_CUDA(cudaStreamSynchronize(st));
         return tgs_launch_render_fwd(cam, s, bv, iv, capacity, out_color, out_depth, out_alpha, touch_target, residual_out, st);
     };
@@ -249,7 +249,7 @@ extern "C" int tgs_forward(const TgsSettings* s, const TgsGaussians* g, tgs_allo
         if (!temp) { tgs_set_error("allocator returned NULL"); return TGS_ENOMEM; }
         rc = tgs_launch_preprocess(cam, s, g, gv, radii, st); if (rc) return rc;
         rc = tgs_depth_order(gv, N, st); if (rc) return rc;
-        rc = tgs_bin_count(gv, N, cam.Tx, cam.Ty, temp, iv.ranges, iv.count, st); if (rc) return rc;
+        rc = tgs_bin_count(gv, N, cam.Tx, cam.Ty, cam.row0, cam.row1, temp, iv.ranges, iv.count, st); if (rc) return rc;
         TGS_CUDA(cudaMemcpyAsync(hp, iv.count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         if (s->rendered_hint > 0) {
             // SPECULATIVE: enqueue scatter + pack + render for `hint` slots, THEN wait for the count (event recorded
@@ -269,7 +269,7 @@ extern "C" int tgs_forward(const TgsSettings* s, const TgsGaussians* g, tgs_allo
             rc = tail(I, I, false); if (rc) return rc;
         }
     } else {
-        rc = tgs_bin_count(gv, 0, cam.Tx, cam.Ty, nullptr, iv.ranges, iv.count, st); if (rc) return rc;
+        rc = tgs_bin_count(gv, 0, cam.Tx, cam.Ty, cam.row0, cam.row1, nullptr, iv.ranges, iv.count, st); if (rc) return rc;
         rc = tail(0, 0, false); if (rc) return rc;
     }
     saved->geom = geom; saved->binning = binning; saved->image = image; saved->num_rendered = I; saved->capacity = cap;

@@ -30,13 +30,14 @@
 // 12 B x chunks x T of count-matrix traffic (0.1 GB at c3).
 #include "tgs_common.cuh"
 #include <cub/cub.cuh>
+#include <cstdlib>
 
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kCountCells = 16384;      // 64 KB difference array per count CTA (c3: 69 x 121 cells = 33 KB, one band)
 
-struct Bands { int rows; int n; int tiles; };   // tile rows per band, number of bands, rows * Tx
+struct Bands { int rows; int n; int tiles; };   // tile rows per band, number of bands (over the RENDERED rows), rows * Tx
 struct Plan {
     int chunk;           // Gaussians per chunk (depth ranks)
     int nchunks;
@@ -53,6 +54,7 @@ Bands make_bands(int max_tiles, int Tx, int Ty) {
     b.tiles = b.rows * Tx;
     return b;
 }
+// Ty = number of tile rows this rank renders (its band of the tile-row shard, or the whole image)
 Plan make_plan(int N, int Tx, int Ty) {
     Plan p;
     p.chunk = 1024;
@@ -65,7 +67,13 @@ Plan make_plan(int N, int Tx, int Ty) {
     if (p.count.rows > Ty) p.count.rows = Ty;
     p.count.n = (Ty + p.count.rows - 1) / p.count.rows;
     p.count.tiles = (p.count.rows + 1) * (Tx + 1);       // cells, not tiles
-    p.scatter = make_bands(TGS_BIN_SCATTER_TILES, Tx, Ty);
+    static int scatter_tiles = 0;                        // tunable for experiments: TGS_SCATTER_TILES=<tiles per band>
+    if (scatter_tiles == 0) {
+        const char* e = getenv("TGS_SCATTER_TILES");
+        scatter_tiles = e ? atoi(e) : TGS_BIN_SCATTER_TILES;
+        if (scatter_tiles < 32 || scatter_tiles > TGS_BIN_BAND_TILES) scatter_tiles = TGS_BIN_SCATTER_TILES;
+    }
+    p.scatter = make_bands(scatter_tiles, Tx, Ty);
     return p;
 }
 
@@ -95,11 +103,11 @@ __device__ __forceinline__ uint32_t magic_of(uint32_t w) { return w > 1 ? (uint3
 // turns them into coverage counts: 4 atomics per Gaussian instead of ~11 (c3) / ~33 (c5).
 __global__ void __launch_bounds__(256)
 k_bin_count(int N, int chunk, const uint32_t* __restrict__ order, const uint32_t* __restrict__ tiles,
-            const uint2* __restrict__ rect, int Tx, int Ty, int rows_per_band, int T, uint32_t* __restrict__ cnt,
-            uint2* __restrict__ span_sorted) {
+            const uint2* __restrict__ rect, int Tx, int row_begin, int row_end, int rows_per_band, int T,
+            uint32_t* __restrict__ cnt, uint2* __restrict__ span_sorted) {
     extern __shared__ int diff[];                      // [(rows+1)][Tx+1]
     const int band = blockIdx.y;
-    const int r0 = band * rows_per_band, r1 = min(Ty, r0 + rows_per_band);
+    const int r0 = row_begin + band * rows_per_band, r1 = min(row_end, r0 + rows_per_band);
     const int rows = r1 - r0, S = Tx + 1;
     for (int t = threadIdx.x; t < (rows + 1) * S; t += 256) diff[t] = 0;
     __syncthreads();
@@ -155,14 +163,14 @@ k_bin_count(int N, int chunk, const uint32_t* __restrict__ order, const uint32_t
 // ---- 2a. per tile column: exclusive prefix over the chunks (in place) and the column total.
 // CTA = 32 tile columns x 8 chunk slices (a warp reads one 128-byte row segment per chunk).
 __global__ void __launch_bounds__(256)
-k_bin_prefix(int nchunks, int T, uint32_t* __restrict__ cnt, uint32_t* __restrict__ totals) {
+k_bin_prefix(int nchunks, int T, int t_begin, int t_end, uint32_t* __restrict__ cnt, uint32_t* __restrict__ totals) {
     __shared__ uint32_t part[8][32];
     const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-    const int t = blockIdx.x * 32 + lane;
+    const int t = t_begin + blockIdx.x * 32 + lane;
     const int per = (nchunks + 7) / 8;
     const int c0 = slice * per, c1 = min(nchunks, c0 + per);
     uint32_t s = 0;
-    if (t < T) {
+    if (t < t_end) {
         const uint32_t* p = cnt + (size_t)c0 * T + t;
 #pragma unroll 8
         for (int c = c0; c < c1; ++c, p += T) s += *p;
@@ -171,7 +179,7 @@ k_bin_prefix(int nchunks, int T, uint32_t* __restrict__ cnt, uint32_t* __restric
     __syncthreads();
     uint32_t run = 0;
     for (int k = 0; k < slice; ++k) run += part[k][lane];
-    if (t < T) {
+    if (t < t_end) {
         if (slice == 7) totals[t] = run + s;
         uint32_t* p = cnt + (size_t)c0 * T + t;
 #pragma unroll 4
@@ -182,14 +190,15 @@ k_bin_prefix(int nchunks, int T, uint32_t* __restrict__ cnt, uint32_t* __restric
 // ---- 2b. tile starts: exclusive scan of the column totals -> ranges, and the instance count.  One CTA.
 // count_out[0] = num_rendered (low 32 bits), count_out[1] = 1 if it does not fit 32 bits.
 __global__ void __launch_bounds__(1024)
-k_bin_ranges(int T, const uint32_t* __restrict__ totals, uint2* __restrict__ ranges, uint32_t* __restrict__ count_out) {
+k_bin_ranges(int T, int t_begin, int t_end, const uint32_t* __restrict__ totals, uint2* __restrict__ ranges,
+             uint32_t* __restrict__ count_out) {
     __shared__ unsigned long long warp_excl[32];
     __shared__ unsigned long long block_total;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long carry = 0;                      // running total of the tiles in front (same in every thread)
     for (int base = 0; base < T; base += 1024) {
         const int t = base + threadIdx.x;
-        const unsigned long long v = t < T ? totals[t] : 0u;
+        const unsigned long long v = (t >= t_begin && t < t_end) ? totals[t] : 0u;   // nothing outside the rendered rows
         unsigned long long inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -234,26 +243,43 @@ k_bin_ranges(int T, const uint32_t* __restrict__ totals, uint2* __restrict__ ran
 // tiles of one rectangle are distinct, so the lanes bump the cursors with plain LDS / STS (no atomics); __syncwarp
 // orders one Gaussian's bumps before the next one's.
 struct __align__(16) Staged { uint32_t base, w, magic, area; };   // base = (y0 - r0) * Tx + x0
-__global__ void __launch_bounds__(32)
-k_bin_scatter(int N, int chunk, const uint32_t* __restrict__ order, const uint2* __restrict__ span_sorted, int Tx, int Ty,
-              int rows_per_band, int T, const uint32_t* __restrict__ cnt, const uint2* __restrict__ ranges, uint32_t cap,
+#if defined(TGS_EXP_NOSYNC)
+#define WALK_SYNC() asm volatile("" ::: "memory")
+#else
+#define WALK_SYNC() __syncwarp()
+#endif
+#if defined(TGS_EXP_NOSTORE)
+#define WALK_STORE(pos, gid) do { if ((pos) == 0xFFFFFFFFu) vals[0] = (gid); } while (0)
+#else
+#define WALK_STORE(pos, gid) do { if ((pos) < cap) vals[(pos)] = (gid); } while (0)
+#endif
+constexpr int kScatterWarps = 1;                       // (chunk, band) units per CTA; measured: 1 beats 4 (0.155 vs 0.176 ms at c3)
+__global__ void __launch_bounds__(32 * kScatterWarps)
+k_bin_scatter(int N, int chunk, int nbands, int nunits, const uint32_t* __restrict__ order,
+              const uint2* __restrict__ span_sorted, int Tx, int row_begin, int row_end, int rows_per_band, int T,
+              const uint32_t* __restrict__ cnt, const uint2* __restrict__ ranges, uint32_t cap,
               uint32_t* __restrict__ vals) {
     extern __shared__ __align__(16) uint32_t smem_u32[];
-    __shared__ Staged stage[32];
-    __shared__ uint32_t stage_id[32];
-    uint32_t* cursor = smem_u32;                       // [band tiles]
-    const int lane = threadIdx.x;
-    const int band = blockIdx.y;
-    const int r0 = band * rows_per_band, r1 = min(Ty, r0 + rows_per_band);
+    __shared__ Staged stage_all[kScatterWarps][32];
+    __shared__ uint32_t stage_id_all[kScatterWarps][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int unit = blockIdx.x * kScatterWarps + warp;
+    if (unit >= nunits) return;                        // warps are independent: no block-level barrier anywhere
+    const int chunk_id = unit / nbands, band = unit - chunk_id * nbands;
+    Staged* stage = stage_all[warp];
+    uint32_t* stage_id = stage_id_all[warp];
+    const int per_warp = rows_per_band * Tx + (chunk + 1) / 2;          // u32 words: cursors + u16 hit list
+    uint32_t* cursor = smem_u32 + (size_t)warp * per_warp;             // [band tiles]
+    const int r0 = row_begin + band * rows_per_band, r1 = min(row_end, r0 + rows_per_band);
     const int nt = (r1 - r0) * Tx;
     uint16_t* hits = reinterpret_cast<uint16_t*>(cursor + rows_per_band * Tx);   // [chunk]
     {   // cursor[t] = start of tile t + instances of the chunks in front of this one
-        const uint32_t* row = cnt + (size_t)blockIdx.x * T + (size_t)r0 * Tx;
+        const uint32_t* row = cnt + (size_t)chunk_id * T + (size_t)r0 * Tx;
         const uint2* rg = ranges + (size_t)r0 * Tx;
 #pragma unroll 4
         for (int t = lane; t < nt; t += 32) cursor[t] = rg[t].x + row[t];
     }
-    const int first = blockIdx.x * chunk, last = min(N, first + chunk);
+    const int first = chunk_id * chunk, last = min(N, first + chunk);
     // ---- phase 1 (throughput): which Gaussians of the chunk touch this band?  Ordered compaction by ballot.
     int nh = 0;
     for (int base = first; base < last; base += 128) {
@@ -273,30 +299,66 @@ k_bin_scatter(int N, int chunk, const uint32_t* __restrict__ order, const uint2*
         }
     }
     __syncwarp();
-    // ---- phase 2 (latency): walk the hits IN ORDER
+    // ---- phase 2 (latency): walk the hits IN ORDER.  32 hits are staged at a time; hits (2j, 2j+1) whose clipped
+    // rectangles hold <= 16 tiles each and do NOT overlap are bumped TOGETHER, one per half warp (disjoint tiles: the
+    // order between the two cannot be observed), which halves the length of the sequential chain; any other pair takes
+    // two steps.
     for (int hb = 0; hb < nh; hb += 32) {
         const int e = hb + lane;
         const int n = min(32, nh - hb);
+        RectClip c; c.w = c.h = c.x0 = c.y0 = 0;
+        uint32_t id = 0;
         if (e < nh) {
             const int r = first + (int)hits[e];
-            const RectClip c = clip_rect(span_sorted[r], r0, r1);
+            c = clip_rect(span_sorted[r], r0, r1);
+            id = order[r];
+        }
+        const uint32_t area = c.w * c.h;
+        {   // can this hit share a step with its pair partner (lane ^ 1)?
+            const uint32_t px0 = __shfl_xor_sync(kFull, c.x0, 1), pw = __shfl_xor_sync(kFull, c.w, 1);
+            const uint32_t py0 = __shfl_xor_sync(kFull, c.y0, 1), ph = __shfl_xor_sync(kFull, c.h, 1);
+            const bool disjoint = (c.x0 + c.w <= px0) || (px0 + pw <= c.x0) || (c.y0 + c.h <= py0) || (py0 + ph <= c.y0);
+            const bool fuse = disjoint && area <= 16 && pw * ph <= 16 && area != 0 && pw * ph != 0;
             Staged sg;
-            sg.base = (c.y0 - (uint32_t)r0) * (uint32_t)Tx + c.x0; sg.w = c.w; sg.magic = magic_of(c.w); sg.area = c.w * c.h;
+            sg.base = (c.y0 - (uint32_t)r0) * (uint32_t)Tx + c.x0; sg.w = c.w; sg.magic = magic_of(c.w);
+            sg.area = area | (fuse ? 0x80000000u : 0u);
             stage[lane] = sg;
-            stage_id[lane] = order[r];
+            stage_id[lane] = id;
         }
         __syncwarp();
-        for (int k = 0; k < n; ++k) {
-            const Staged q = stage[k];
-            const uint32_t gid = stage_id[k];
-            for (uint32_t l = lane; l < q.area; l += 32) {       // one round for rectangles of up to 32 tiles
-                uint32_t xx; const uint32_t yy = div_by(l, q.w, q.magic, xx);
-                const uint32_t t = q.base + yy * (uint32_t)Tx + xx;
-                const uint32_t pos = cursor[t];
-                cursor[t] = pos + 1;
-                if (pos < cap) vals[pos] = gid;                  // speculative mode: never write past the hint
+        for (int k = 0; k < n; k += 2) {
+            const uint32_t fused = stage[k].area >> 31;               // uniform: both partners carry the same flag
+            if (fused) {
+                const int half = lane >> 4;
+                const Staged q = stage[k + half];
+                const uint32_t gid = stage_id[k + half];
+                const uint32_t l = (uint32_t)(lane & 15);
+                if (l < (q.area & 0x7FFFFFFFu)) {
+                    uint32_t xx; const uint32_t yy = div_by(l, q.w, q.magic, xx);
+                    const uint32_t t = q.base + yy * (uint32_t)Tx + xx;
+                    const uint32_t pos = cursor[t];
+                    cursor[t] = pos + 1;
+                    WALK_STORE(pos, gid);                            // speculative mode: never write past the hint
+                }
+                WALK_SYNC();
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (k + h < n) {
+                        const Staged q = stage[k + h];
+                        const uint32_t gid = stage_id[k + h];
+                        const uint32_t a = q.area & 0x7FFFFFFFu;
+                        for (uint32_t l = lane; l < a; l += 32) {    // one round for rectangles of up to 32 tiles
+                            uint32_t xx; const uint32_t yy = div_by(l, q.w, q.magic, xx);
+                            const uint32_t t = q.base + yy * (uint32_t)Tx + xx;
+                            const uint32_t pos = cursor[t];
+                            cursor[t] = pos + 1;
+                            WALK_STORE(pos, gid);
+                        }
+                        WALK_SYNC();                                 // the next Gaussian's bumps come after this one's
+                    }
+                }
             }
-            __syncwarp();                                        // the next Gaussian's bumps come after this one's
         }
     }
 }
@@ -355,7 +417,7 @@ size_t tgs_depth_sort_temp_bytes(int N) {
 }
 
 size_t tgs_bin_temp_bytes(int N, int Tx, int Ty) {
-    const Plan p = make_plan(N, Tx, Ty);
+    const Plan p = make_plan(N, Tx, Ty);               // nchunks does not depend on the rendered rows
     const size_t T = (size_t)Tx * Ty;
     return tgs_align_up((size_t)p.nchunks * T * sizeof(uint32_t)) + tgs_align_up(T * sizeof(uint32_t));
 }
@@ -371,35 +433,37 @@ int tgs_depth_order(GeomView gv, int N, cudaStream_t st) {
 }
 
 // Phases 1-2: count matrix, per-tile prefixes, tile ranges and the instance count (on the device: count_out[0..1]).
-int tgs_bin_count(GeomView gv, int N, int Tx, int Ty, void* temp, uint2* ranges, uint32_t* count_out, cudaStream_t st) {
+int tgs_bin_count(GeomView gv, int N, int Tx, int Ty, int row0, int row1, void* temp, uint2* ranges, uint32_t* count_out,
+                  cudaStream_t st) {
     const int T = Tx * Ty;
-    if (N == 0) {
+    if (N == 0 || row1 <= row0) {
         TGS_CUDA(cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)T, st));
         TGS_CUDA(cudaMemsetAsync(count_out, 0, 2 * sizeof(uint32_t), st));
         return 0;
     }
-    const Plan p = make_plan(N, Tx, Ty);
+    const Plan p = make_plan(N, Tx, row1 - row0);      // bands over the rows this rank renders
     uint32_t* cnt = (uint32_t*)temp;
     uint32_t* totals = (uint32_t*)((char*)temp + tgs_align_up((size_t)p.nchunks * T * sizeof(uint32_t)));
+    const int t_begin = row0 * Tx, t_end = row1 * Tx;
     static bool attr_done[64] = {};
     int dev = 0;
     TGS_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !attr_done[dev]) {
         TGS_CUDA(cudaFuncSetAttribute(k_bin_count, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (TGS_BIN_BAND_TILES + 1) * 4));
-        TGS_CUDA(cudaFuncSetAttribute(k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, TGS_BIN_BAND_TILES * 4 + 8192 * 2));   // one row of a very wide image + the hit list
+        TGS_CUDA(cudaFuncSetAttribute(k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterWarps * (TGS_BIN_BAND_TILES * 4 + 8192 * 2)));   // rows of a very wide image + the hit lists
         attr_done[dev] = true;
     }
     {
         TgsProfScope prof(TGS_STAGE_DUPLICATE, st);
         k_bin_count<<<dim3(p.nchunks, p.count.n), 256, (size_t)p.count.tiles * 4, st>>>(
-            N, p.chunk, gv.order, gv.tiles_touched, gv.rect, Tx, Ty, p.count.rows, T, cnt, gv.span_sorted);
+            N, p.chunk, gv.order, gv.tiles_touched, gv.rect, Tx, row0, row1, p.count.rows, T, cnt, gv.span_sorted);
         tgs_count_own(1);
         TGS_CUDA(cudaGetLastError());
     }
     {
         TgsProfScope prof(TGS_STAGE_SORT, st);
-        k_bin_prefix<<<(T + 31) / 32, 256, 0, st>>>(p.nchunks, T, cnt, totals);
-        k_bin_ranges<<<1, 1024, 0, st>>>(T, totals, ranges, count_out);
+        k_bin_prefix<<<(t_end - t_begin + 31) / 32, 256, 0, st>>>(p.nchunks, T, t_begin, t_end, cnt, totals);
+        k_bin_ranges<<<1, 1024, 0, st>>>(T, t_begin, t_end, totals, ranges, count_out);
         tgs_count_own(2);
         TGS_CUDA(cudaGetLastError());
     }
@@ -409,15 +473,17 @@ int tgs_bin_count(GeomView gv, int N, int Tx, int Ty, void* temp, uint2* ranges,
 // Phases 3-4.  `cap` = instances the binning buffer holds; `count` = instances to pack (== I in exact mode, == cap in
 // speculative mode, where the real count is read on the device from count_dev).
 int tgs_bin_scatter_pack(GeomView gv, BinView bv, int N, int64_t count, int64_t cap, bool speculative, int Tx, int Ty,
-                         const void* temp, const uint2* ranges, const uint32_t* count_dev, cudaStream_t st) {
-    if (count == 0 || N == 0) return 0;
+                         int row0, int row1, const void* temp, const uint2* ranges, const uint32_t* count_dev, cudaStream_t st) {
+    if (count == 0 || N == 0 || row1 <= row0) return 0;
     const int T = Tx * Ty;
-    const Plan p = make_plan(N, Tx, Ty);
+    const Plan p = make_plan(N, Tx, row1 - row0);
     const uint32_t* cnt = (const uint32_t*)temp;
     {
         TgsProfScope prof(TGS_STAGE_BIN_SCATTER, st);
-        k_bin_scatter<<<dim3(p.nchunks, p.scatter.n), 32, (size_t)p.scatter.tiles * 4 + (size_t)p.chunk * 2, st>>>(
-            N, p.chunk, gv.order, gv.span_sorted, Tx, Ty, p.scatter.rows, T, cnt, ranges,
+        const int nunits = p.nchunks * p.scatter.n;
+        const size_t per_warp = ((size_t)p.scatter.tiles + (size_t)(p.chunk + 1) / 2) * 4;
+        k_bin_scatter<<<(nunits + kScatterWarps - 1) / kScatterWarps, 32 * kScatterWarps, per_warp * kScatterWarps, st>>>(
+            N, p.chunk, p.scatter.n, nunits, gv.order, gv.span_sorted, Tx, row0, row1, p.scatter.rows, T, cnt, ranges,
             (uint32_t)(cap > 0xFFFFFFFFll ? 0xFFFFFFFFll : cap), bv.vals_sorted);
         tgs_count_own(1);
         TGS_CUDA(cudaGetLastError());

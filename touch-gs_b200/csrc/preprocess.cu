@@ -53,6 +53,43 @@ __device__ __forceinline__ void warp_stage_out(float* __restrict__ g_base, int f
     }
 }
 
+// Row-wise staging of a FEW Gaussians of the warp (bit k of `mask` = lane k's Gaussian): 12 lanes move one 192-byte row.
+// Used when most of the warp's Gaussians do not need their colour (culled, or outside this rank's tile-row band).
+__device__ __forceinline__ void warp_stage_rows(const float* __restrict__ g_base, int first, float4* s_rows, unsigned mask, int lane) {
+    const float4* src = reinterpret_cast<const float4*>(g_base) + (size_t)first * kShRowF4;
+    while (mask) {
+        const int k0 = __ffs(mask) - 1;
+        mask &= mask - 1;
+        int k1 = -1;
+        if (mask) { k1 = __ffs(mask) - 1; mask &= mask - 1; }
+        // lanes 0..11 take row k0, lanes 16..27 row k1
+        const int k = lane < 16 ? k0 : k1, e = lane & 15;
+        if (k >= 0 && e < kShRowF4) s_rows[k * kShRowPad + e] = __ldg(src + k * kShRowF4 + e);
+    }
+    __syncwarp();
+}
+
+// colour sums of one staged row: four coefficients' worth of floats at a time, each channel accumulated in ascending-k
+// order exactly like tgs_sh_forward (bit-identical), without a 48-register copy of the row.  Shared by the forward and
+// by the backward's recomputation of the clamp mask, so both see the same bits.
+__device__ __forceinline__ void staged_row_color(const float4* s_row, const float* b, int deg, float* acc) {
+    acc[0] = acc[1] = acc[2] = 0.0f;
+    const int nf = 3 * (deg + 1) * (deg + 1);
+#pragma unroll
+    for (int k4 = 0; k4 < kShRowF4; ++k4) {
+        if (4 * k4 < nf) {
+            const float4 v = s_row[k4];
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int e = 4 * k4 + j;
+                if (e < nf) acc[e % 3] += b[e / 3] * vv[j];
+            }
+        }
+    }
+}
+#define TGS_CLAMP_UNKNOWN 0x80u   /* clamp-mask byte of a visible Gaussian whose colour this rank did not evaluate */
+
 template <bool STAGE>
 __global__ void __launch_bounds__(kBlock)
 k_preprocess(int N, const float* __restrict__ means, const float* __restrict__ scales,
@@ -68,54 +105,55 @@ k_preprocess(int N, const float* __restrict__ means, const float* __restrict__ s
     extern __shared__ __align__(16) float4 s_stage[];
     load_cam(vm, pm, campos, &cm);
     int i = blockIdx.x * kBlock + threadIdx.x;
-    float4* s_row = nullptr;
-    if (STAGE) {                                // every warp stages the SH block of its 32 Gaussians (K = 16)
+    const bool inN = i < N;
+    float x = 0.f, y = 0.f, z = 0.f;
+    float cov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    TgsProj p;
+    bool vis = false;
+    if (inN) {
+        x = means[3 * i]; y = means[3 * i + 1]; z = means[3 * i + 2];
+        if (covpre) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) cov[k] = covpre[6 * i + k];
+        } else {
+            float4 q = reinterpret_cast<const float4*>(rots)[i];
+            float sc[3] = {scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]};
+            float qq[4] = {q.x, q.y, q.z, q.w};
+            tgs_cov3d(sc, cam.mod, qq, cov);
+        }
+        vis = tgs_project(cm.vm, cm.pm, cam, x, y, z, cov, p);
+    }
+    float rgb[3] = {0.f, 0.f, 0.f};
+    unsigned cl = 0;
+    if (STAGE) {
+        // The colour is consumed only by the instances a Gaussian emits ON THIS RANK (p.tiles > 0: inside the tile-row
+        // band), so only those read their 192-byte SH row (K = 16) -- culled Gaussians and, on a tile-row shard, the
+        // (g-1)/g of the scene outside the band skip it.  The warp stages its whole 6 KB block with coalesced loads when
+        // most rows are needed, else row by row.  A visible Gaussian without colour gets the clamp mask "unknown": the
+        // backward (which runs for every visible Gaussian on every rank) recomputes it from the row it stages anyway.
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         float4* s_rows = s_stage + (size_t)warp * 32 * kShRowPad;
         const int first = blockIdx.x * kBlock + warp * 32;
-        if (first < N) warp_stage_in(shs, first, N, s_rows, lane);
-        s_row = s_rows + lane * kShRowPad;
-    }
-    if (i >= N) return;
-    float x = means[3 * i], y = means[3 * i + 1], z = means[3 * i + 2];
-    float cov[6];
-    if (covpre) {
+        const bool need = vis && p.tiles > 0;
+        const unsigned m = __ballot_sync(0xffffffffu, need);
+        if (__popc(m) > 12) warp_stage_in(shs, first, N, s_rows, lane);
+        else if (m) warp_stage_rows(shs, first, s_rows, m, lane);
+        if (need) {
+            float b[16], acc[3];
+            tgs_sh_bases(cam.deg, x - cm.cp[0], y - cm.cp[1], z - cm.cp[2], b);
+            staged_row_color(s_rows + lane * kShRowPad, b, cam.deg, acc);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) cov[k] = covpre[6 * i + k];
-    } else {
-        float4 q = reinterpret_cast<const float4*>(rots)[i];
-        float sc[3] = {scales[3 * i], scales[3 * i + 1], scales[3 * i + 2]};
-        float qq[4] = {q.x, q.y, q.z, q.w};
-        tgs_cov3d(sc, cam.mod, qq, cov);
-    }
-    TgsProj p;
-    bool vis = tgs_project(cm.vm, cm.pm, cam, x, y, z, cov, p);
-    float rgb[3] = {0.f, 0.f, 0.f};
-    unsigned cl = 0;
-    if (vis && shs && STAGE) {
-        // colour straight from the staged row: four coefficients' worth of floats at a time, each channel accumulated
-        // in ascending-k order exactly like tgs_sh_forward (bit-identical), without a 48-register copy of the row
-        float b[16], acc[3] = {0.f, 0.f, 0.f};
-        tgs_sh_bases(cam.deg, x - cm.cp[0], y - cm.cp[1], z - cm.cp[2], b);
-        const int nf = 3 * (cam.deg + 1) * (cam.deg + 1);
-#pragma unroll
-        for (int k4 = 0; k4 < kShRowF4; ++k4) {
-            if (4 * k4 < nf) {
-                const float4 v = s_row[k4];
-                const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int e = 4 * k4 + j;
-                    if (e < nf) acc[e % 3] += b[e / 3] * vv[j];
-                }
+            for (int c = 0; c < 3; ++c) {
+                float a = acc[c] + 0.5f;
+                if (a < 0.0f) { cl |= (1u << c); a = 0.0f; }
+                rgb[c] = a;
             }
+        } else if (vis) {
+            cl = TGS_CLAMP_UNKNOWN;
         }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float a = acc[c] + 0.5f;
-            if (a < 0.0f) { cl |= (1u << c); a = 0.0f; }
-            rgb[c] = a;
-        }
+    }
+    if (!inN) return;
+    if (STAGE) {
     } else if (vis) {
         if (shs && !STAGE) {
             // K*3 contiguous floats per Gaussian; 16-byte loads (K*12 B is a multiple of 16 for K in {1,4,9,16}
@@ -230,7 +268,19 @@ k_preprocess_bwd(int N, PeerGather pg, const TgsRecord* __restrict__ rec, const 
         if (shs) {
             if (STAGE) {
                 float* row = reinterpret_cast<float*>(s_rows + lane * kShRowPad);
-                tgs_sh_backward(cam.deg, cam.K, row, x - cm.cp[0], y - cm.cp[1], z - cm.cp[2], sg + 6, clamped[i], row, dm,
+                unsigned cl = clamped[i];
+                if (cl & TGS_CLAMP_UNKNOWN) {
+                    // this rank's forward did not evaluate the colour (the Gaussian lies outside its tile-row band):
+                    // recompute the clamp mask from the staged row with the forward's own arithmetic
+                    float b[16], acc[3];
+                    tgs_sh_bases(cam.deg, x - cm.cp[0], y - cm.cp[1], z - cm.cp[2], b);
+                    staged_row_color(s_rows + lane * kShRowPad, b, cam.deg, acc);
+                    cl = 0;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        if (acc[c] + 0.5f < 0.0f) cl |= (1u << c);
+                }
+                tgs_sh_backward(cam.deg, cam.K, row, x - cm.cp[0], y - cm.cp[1], z - cm.cp[2], sg + 6, cl, row, dm,
                                 false);
             } else {
                 // streams the K coefficients in groups of 4 straight from / to global memory

@@ -163,7 +163,7 @@ extern "C" int tgs_rasterize_screen_forward(const TgsSettings* s, int32_t N, con
         temp = alloc(user, TGS_BUF_TEMP, tgs_bin_temp_bytes(N, cam.Tx, cam.Ty));
         if (!temp) { tgs_set_error("allocator returned NULL"); return TGS_ENOMEM; }
     }
-    int rc = tgs_bin_count(gv, N, cam.Tx, cam.Ty, temp, iv.ranges, iv.count, st); if (rc) return rc;
+    int rc = tgs_bin_count(gv, N, cam.Tx, cam.Ty, cam.row0, cam.row1, temp, iv.ranges, iv.count, st); if (rc) return rc;
     if (N > 0) {
         uint32_t h_I[2] = {0, 0};
         TGS_CUDA(cudaMemcpyAsync(h_I, iv.count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -175,7 +175,7 @@ extern "C" int tgs_rasterize_screen_forward(const TgsSettings* s, int32_t N, con
     void* binning = alloc(user, TGS_BUF_BINNING, bl.total);
     if (!binning) { tgs_set_error("allocator returned NULL"); return TGS_ENOMEM; }
     BinView bv = tgs_bin_view(binning, I);
-    rc = tgs_bin_scatter_pack(gv, bv, N, I, I, false, cam.Tx, cam.Ty, temp, iv.ranges, iv.count, st); if (rc) return rc;
+    rc = tgs_bin_scatter_pack(gv, bv, N, I, I, false, cam.Tx, cam.Ty, cam.row0, cam.row1, temp, iv.ranges, iv.count, st); if (rc) return rc;
     TgsSettings s2 = *s;
     s2.depth_normalize = 0;
     rc = tgs_launch_render_fwd(cam, &s2, bv, iv, I, out_color, out_depth, out_alpha, nullptr, nullptr, st); if (rc) return rc;

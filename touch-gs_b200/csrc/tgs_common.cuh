@@ -76,7 +76,7 @@ struct ImageView {
     uint32_t* count;         // [2] num_rendered (device copy), overflow flag
 };
 #define TGS_BIN_BAND_TILES 8192     /* tiles per band of the count kernel: 32 KB of shared-memory counters */
-#define TGS_BIN_SCATTER_TILES 1024  /* tiles per band of the ordered scatter (one warp per (chunk, band)) */
+#define TGS_BIN_SCATTER_TILES 256   /* tiles per band of the ordered scatter (one warp per (chunk, band)): measured best at c3 */
 GeomView tgs_geom_view(void* base, int N);
 BinView tgs_bin_view(void* base, int64_t I);
 ImageView tgs_image_view(void* base, int W, int H);
@@ -96,11 +96,12 @@ int tgs_launch_mark_visible(int N, const float* means, const float* vm, uint8_t*
 // binning.cu
 int tgs_depth_order(GeomView gv, int N, cudaStream_t st);
 // count matrix + per-tile prefixes + ranges + instance count (device: count_out[0] = I, count_out[1] = overflow flag)
-int tgs_bin_count(GeomView gv, int N, int Tx, int Ty, void* temp, uint2* ranges, uint32_t* count_out, cudaStream_t st);
+int tgs_bin_count(GeomView gv, int N, int Tx, int Ty, int row0, int row1, void* temp, uint2* ranges, uint32_t* count_out,
+                  cudaStream_t st);
 // `cap` = instances the binning buffer holds; `count` = instances to pack (== I in exact mode, == cap in speculative
 // mode, where the real count is read on the device from count_dev)
 int tgs_bin_scatter_pack(GeomView gv, BinView bv, int N, int64_t count, int64_t cap, bool speculative, int Tx, int Ty,
-                         const void* temp, const uint2* ranges, const uint32_t* count_dev, cudaStream_t st);
+                         int row0, int row1, const void* temp, const uint2* ranges, const uint32_t* count_dev, cudaStream_t st);
 // render.cu
 int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, BinView bv, ImageView iv, int64_t capacity,
                           float* out_color, float* out_depth, float* out_alpha,
