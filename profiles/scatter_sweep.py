@@ -1,6 +1,6 @@
 import os, sys, json, subprocess
 sys.path.insert(0, '.')
-for tiles in (256, 1024):
+for tiles in (0, 1024):
     for rows in ("0,68", "0,34", "0,9"):
         env = dict(os.environ, TGS_SCATTER_TILES=str(tiles))
         code = f"""

@@ -156,8 +156,8 @@ ImageView tgs_image_view(void* base, int W, int H) {
 static int check_inputs(const TgsSettings* s, const TgsGaussians* g) {
     if (!s || !g) { tgs_set_error("NULL settings / gaussians"); return TGS_EINVAL; }
     if (s->image_width <= 0 || s->image_height <= 0) { tgs_set_error("bad image size %dx%d", s->image_width, s->image_height); return TGS_EINVAL; }
-    if (s->image_width > TGS_BIN_BAND_TILES * TGS_TILE || s->image_height > 65535 * TGS_TILE) {
-        tgs_set_error("image too large (width <= %d, height <= %d)", TGS_BIN_BAND_TILES * TGS_TILE, 65535 * TGS_TILE); return TGS_EINVAL; }
+    if (s->image_width > TGS_BIN_SCATTER_MAX_TX * TGS_TILE || s->image_height > 65535 * TGS_TILE) {
+        tgs_set_error("image too large (width <= %d, height <= %d)", TGS_BIN_SCATTER_MAX_TX * TGS_TILE, 65535 * TGS_TILE); return TGS_EINVAL; }
     if (g->N < 0) { tgs_set_error("negative N"); return TGS_EINVAL; }
     if (!s->viewmatrix || !s->projmatrix || !s->bg) { tgs_set_error("viewmatrix / projmatrix / bg must be non-NULL"); return TGS_EINVAL; }
     if (g->N > 0) {

@@ -55,7 +55,7 @@ Bands make_bands(int max_tiles, int Tx, int Ty) {
     return b;
 }
 // Ty = number of tile rows this rank renders (its band of the tile-row shard, or the whole image)
-Plan make_plan(int N, int Tx, int Ty) {
+Plan make_plan(int N, int Tx, int Ty, bool whole_image = true) {
     Plan p;
     p.chunk = 1024;
     while (p.chunk < 8192 && (N + p.chunk - 1) / p.chunk > 1536) p.chunk *= 2;
@@ -67,12 +67,20 @@ Plan make_plan(int N, int Tx, int Ty) {
     if (p.count.rows > Ty) p.count.rows = Ty;
     p.count.n = (Ty + p.count.rows - 1) / p.count.rows;
     p.count.tiles = (p.count.rows + 1) * (Tx + 1);       // cells, not tiles
-    static int scatter_tiles = 0;                        // tunable for experiments: TGS_SCATTER_TILES=<tiles per band>
-    if (scatter_tiles == 0) {
+    // scatter bands: every (chunk, band) unit scans its whole chunk for hits, so the number of bands is kept around
+    // 32 whatever the image size (256 tiles at c3, 1024 at 4K); TGS_SCATTER_TILES=<tiles per band> overrides (experiments)
+    static int env_tiles = -1;
+    if (env_tiles < 0) {
         const char* e = getenv("TGS_SCATTER_TILES");
-        scatter_tiles = e ? atoi(e) : TGS_BIN_SCATTER_TILES;
-        if (scatter_tiles < 32 || scatter_tiles > TGS_BIN_BAND_TILES) scatter_tiles = TGS_BIN_SCATTER_TILES;
+        env_tiles = e ? atoi(e) : 0;
+        if (env_tiles < 32 || env_tiles > TGS_BIN_SCATTER_MAX_TX) env_tiles = 0;
     }
+    // measured at c3: whole image (one warp per unit) best with ~32 bands; a band of a tile-row shard (8 warps per
+    // unit) best with ~4 bands (half image: 1024 tiles 0.09 ms vs 256 tiles 0.136; an eighth: 256 tiles 0.035 ms)
+    int scatter_tiles = (Tx * Ty) / (whole_image ? 32 : 4);
+    if (scatter_tiles < TGS_BIN_SCATTER_TILES) scatter_tiles = TGS_BIN_SCATTER_TILES;
+    if (scatter_tiles > (whole_image ? 4096 : 2048)) scatter_tiles = whole_image ? 4096 : 2048;
+    if (env_tiles) scatter_tiles = env_tiles;
     p.scatter = make_bands(scatter_tiles, Tx, Ty);
     return p;
 }
@@ -235,74 +243,105 @@ k_bin_ranges(int T, int t_begin, int t_end, const uint32_t* __restrict__ totals,
     }
 }
 
-// ---- 3. ordered scatter.  One single-warp CTA per (chunk, band); dynamic shared memory = the band's cursors + the
-// chunk's hit list.  The walk over the chunk's Gaussians is sequential by construction (order inside a tile = order
-// of the walk), so everything around it is organised to keep the walk short: phase 1 finds the Gaussians of the chunk
-// that touch the band (coalesced loads of the depth-ordered rectangles, ordered compaction by ballot), phase 2 walks
-// only those, 32 staged at a time in shared memory (one broadcast LDS.128 per Gaussian instead of shuffles).  The
-// tiles of one rectangle are distinct, so the lanes bump the cursors with plain LDS / STS (no atomics); __syncwarp
-// orders one Gaussian's bumps before the next one's.
+// ---- 3. ordered scatter.  One CTA of kSub warps per (chunk, band); dynamic shared memory = kSub cursor arrays of the
+// band's tiles + the chunk's hit lists.
+// The walk that assigns positions is sequential by construction (order inside a tile = order of the walk), and
+// depth-consecutive Gaussians cluster on screen, so a few (chunk, band) units hold several times the average number
+// of hits: a single walker per unit leaves the kernel waiting for its longest chain.  The chunk is therefore cut into
+// kSub sub-chunks of consecutive ranks, one per warp, with the SAME counting idea one level down:
+//   phase 1 (throughput): each warp finds the Gaussians of its sub-chunk that touch the band (coalesced loads of the
+//            depth-ordered rectangles, ordered compaction by ballot) and COUNTS their coverage per tile into its own
+//            array (order-free: one lane per hit, shared-memory atomics);
+//   prefix:  per tile, exclusive prefix over the warps + the tile's start + the chunks in front (count matrix row)
+//            turns the count arrays into the warps' private cursors;
+//   phase 2 (latency): each warp walks ITS hits in order, 32 staged at a time (one broadcast LDS.128 per Gaussian);
+//            the tiles of one rectangle are distinct, so the lanes bump the cursors with plain LDS / STS; hits
+//            (2j, 2j+1) with <= 16 tiles each and disjoint rectangles are bumped together, one per half warp.
 struct __align__(16) Staged { uint32_t base, w, magic, area; };   // base = (y0 - r0) * Tx + x0
-#if defined(TGS_EXP_NOSYNC)
-#define WALK_SYNC() asm volatile("" ::: "memory")
-#else
-#define WALK_SYNC() __syncwarp()
-#endif
-#if defined(TGS_EXP_NOSTORE)
-#define WALK_STORE(pos, gid) do { if ((pos) == 0xFFFFFFFFu) vals[0] = (gid); } while (0)
-#else
-#define WALK_STORE(pos, gid) do { if ((pos) < cap) vals[(pos)] = (gid); } while (0)
-#endif
-constexpr int kScatterWarps = 1;                       // (chunk, band) units per CTA; measured: 1 beats 4 (0.155 vs 0.176 ms at c3)
-__global__ void __launch_bounds__(32 * kScatterWarps)
-k_bin_scatter(int N, int chunk, int nbands, int nunits, const uint32_t* __restrict__ order,
-              const uint2* __restrict__ span_sorted, int Tx, int row_begin, int row_end, int rows_per_band, int T,
-              const uint32_t* __restrict__ cnt, const uint2* __restrict__ ranges, uint32_t cap,
-              uint32_t* __restrict__ vals) {
+// kSub = warps (sub-chunks) per (chunk, band) unit.  8 when a rank renders a band of the image (tile-row shard: few,
+// skewed units -> the longest chain decides), 1 for a whole image (many units: throughput decides, and a lone warp
+// needs no counting pass: its cursors start at the tile starts + the chunks in front).  Measured at c3:
+// whole image 0.155 ms (kSub 1) vs 0.19-0.34 (kSub 8); an eighth of the image 0.035 ms (kSub 8) vs 0.09 (kSub 1).
+template <int kSub>
+__global__ void __launch_bounds__(32 * kSub)
+k_bin_scatter(int N, int chunk, int nbands, const uint32_t* __restrict__ order, const uint2* __restrict__ span_sorted,
+              int Tx, int row_begin, int row_end, int rows_per_band, int T, const uint32_t* __restrict__ cnt,
+              const uint2* __restrict__ ranges, uint32_t cap, uint32_t* __restrict__ vals) {
     extern __shared__ __align__(16) uint32_t smem_u32[];
-    __shared__ Staged stage_all[kScatterWarps][32];
-    __shared__ uint32_t stage_id_all[kScatterWarps][32];
+    __shared__ Staged stage_all[kSub][32];
+    __shared__ uint32_t stage_id_all[kSub][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int unit = blockIdx.x * kScatterWarps + warp;
-    if (unit >= nunits) return;                        // warps are independent: no block-level barrier anywhere
-    const int chunk_id = unit / nbands, band = unit - chunk_id * nbands;
+    const int chunk_id = blockIdx.x / nbands, band = blockIdx.x - chunk_id * nbands;
     Staged* stage = stage_all[warp];
     uint32_t* stage_id = stage_id_all[warp];
-    const int per_warp = rows_per_band * Tx + (chunk + 1) / 2;          // u32 words: cursors + u16 hit list
-    uint32_t* cursor = smem_u32 + (size_t)warp * per_warp;             // [band tiles]
+    const int band_tiles = rows_per_band * Tx;
+    const int sub = chunk / kSub;                       // ranks per warp (chunk is a multiple of 32 * kSub)
+    uint32_t* cursor = smem_u32 + (size_t)warp * band_tiles;                                        // [kSub][band tiles]
+    uint16_t* hits = reinterpret_cast<uint16_t*>(smem_u32 + (size_t)kSub * band_tiles) + (size_t)warp * sub;   // [kSub][sub]
     const int r0 = row_begin + band * rows_per_band, r1 = min(row_end, r0 + rows_per_band);
     const int nt = (r1 - r0) * Tx;
-    uint16_t* hits = reinterpret_cast<uint16_t*>(cursor + rows_per_band * Tx);   // [chunk]
-    {   // cursor[t] = start of tile t + instances of the chunks in front of this one
-        const uint32_t* row = cnt + (size_t)chunk_id * T + (size_t)r0 * Tx;
-        const uint2* rg = ranges + (size_t)r0 * Tx;
-#pragma unroll 4
-        for (int t = lane; t < nt; t += 32) cursor[t] = rg[t].x + row[t];
+    if (kSub > 1) {
+        for (int t = lane; t < nt; t += 32) cursor[t] = 0;
+        __syncwarp();
     }
-    const int first = chunk_id * chunk, last = min(N, first + chunk);
-    // ---- phase 1 (throughput): which Gaussians of the chunk touch this band?  Ordered compaction by ballot.
+    const int first = chunk_id * chunk + warp * sub, last = min(N, first + sub);
+    // ---- phase 1: hits of this warp's sub-chunk + their coverage counts
     int nh = 0;
     for (int base = first; base < last; base += 128) {
-        uint32_t ys[4];
+        uint2 sp[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {                  // four independent coalesced loads in flight
             const int r = base + 32 * k + lane;
-            ys[k] = r < last ? span_sorted[r].y : 0u;
+            sp[k] = r < last ? span_sorted[r] : make_uint2(0u, 0u);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int y0 = (int)(ys[k] & 0xFFFF), y1 = (int)(ys[k] >> 16);
-            const bool hit = max(y0, r0) < min(y1, r1);
+            const RectClip c = clip_rect(sp[k], r0, r1);
+            const bool hit = c.w != 0 && c.h != 0;
             const unsigned m = __ballot_sync(kFull, hit);
+            const uint32_t area = c.w * c.h;
+            const uint32_t t0 = (c.y0 - (uint32_t)r0) * (uint32_t)Tx + c.x0;
             if (hit) hits[nh + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(base - first + 32 * k + lane);
             nh += __popc(m);
+            if (kSub == 1) continue;                       // a lone walker needs no counts
+            if (hit) {
+                if (area <= 64) {                          // small rectangles: the owning lane counts its own tiles
+                    uint32_t t = t0;
+                    for (uint32_t y = 0; y < c.h; ++y, t += Tx)
+                        for (uint32_t x = 0; x < c.w; ++x) atomicAdd(&cursor[t + x], 1u);
+                }
+            }
+            unsigned big = __ballot_sync(kFull, hit && area > 64);
+            while (big) {                                  // large rectangles: the whole warp counts them together
+                const int j = __ffs(big) - 1;
+                big &= big - 1;
+                const uint32_t bt = __shfl_sync(kFull, t0, j), bw = __shfl_sync(kFull, c.w, j), ba = __shfl_sync(kFull, area, j);
+                const uint32_t bm = magic_of(bw);
+                for (uint32_t l = lane; l < ba; l += 32) {
+                    uint32_t xx; const uint32_t yy = div_by(l, bw, bm, xx);
+                    atomicAdd(&cursor[bt + yy * (uint32_t)Tx + xx], 1u);
+                }
+            }
         }
     }
-    __syncwarp();
-    // ---- phase 2 (latency): walk the hits IN ORDER.  32 hits are staged at a time; hits (2j, 2j+1) whose clipped
-    // rectangles hold <= 16 tiles each and do NOT overlap are bumped TOGETHER, one per half warp (disjoint tiles: the
-    // order between the two cannot be observed), which halves the length of the sequential chain; any other pair takes
-    // two steps.
+    if (kSub > 1) __syncthreads(); else __syncwarp();
+    {   // ---- prefix over the warps: cursor_w[t] = start of tile t + chunks in front + sub-chunks in front
+        const uint32_t* row = cnt + (size_t)chunk_id * T + (size_t)r0 * Tx;
+        const uint2* rg = ranges + (size_t)r0 * Tx;
+#pragma unroll 4
+        for (int t = threadIdx.x; t < nt; t += 32 * kSub) {
+            uint32_t run = rg[t].x + row[t];
+#pragma unroll
+            for (int w = 0; w < kSub; ++w) {
+                uint32_t* p = smem_u32 + (size_t)w * band_tiles + t;
+                const uint32_t v = kSub > 1 ? *p : 0u;
+                *p = run;
+                run += v;
+            }
+        }
+    }
+    if (kSub > 1) __syncthreads(); else __syncwarp();
+    // ---- phase 2: walk this warp's hits IN ORDER
     for (int hb = 0; hb < nh; hb += 32) {
         const int e = hb + lane;
         const int n = min(32, nh - hb);
@@ -338,9 +377,9 @@ k_bin_scatter(int N, int chunk, int nbands, int nunits, const uint32_t* __restri
                     const uint32_t t = q.base + yy * (uint32_t)Tx + xx;
                     const uint32_t pos = cursor[t];
                     cursor[t] = pos + 1;
-                    WALK_STORE(pos, gid);                            // speculative mode: never write past the hint
+                    if (pos < cap) vals[pos] = gid;                  // speculative mode: never write past the hint
                 }
-                WALK_SYNC();
+                __syncwarp();
             } else {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -353,9 +392,9 @@ k_bin_scatter(int N, int chunk, int nbands, int nunits, const uint32_t* __restri
                             const uint32_t t = q.base + yy * (uint32_t)Tx + xx;
                             const uint32_t pos = cursor[t];
                             cursor[t] = pos + 1;
-                            WALK_STORE(pos, gid);
+                            if (pos < cap) vals[pos] = gid;
                         }
-                        WALK_SYNC();                                 // the next Gaussian's bumps come after this one's
+                        __syncwarp();                                // the next Gaussian's bumps come after this one's
                     }
                 }
             }
@@ -441,7 +480,7 @@ int tgs_bin_count(GeomView gv, int N, int Tx, int Ty, int row0, int row1, void* 
         TGS_CUDA(cudaMemsetAsync(count_out, 0, 2 * sizeof(uint32_t), st));
         return 0;
     }
-    const Plan p = make_plan(N, Tx, row1 - row0);      // bands over the rows this rank renders
+    const Plan p = make_plan(N, Tx, row1 - row0, row0 == 0 && row1 == Ty);      // bands over the rows this rank renders
     uint32_t* cnt = (uint32_t*)temp;
     uint32_t* totals = (uint32_t*)((char*)temp + tgs_align_up((size_t)p.nchunks * T * sizeof(uint32_t)));
     const int t_begin = row0 * Tx, t_end = row1 * Tx;
@@ -450,7 +489,9 @@ int tgs_bin_count(GeomView gv, int N, int Tx, int Ty, int row0, int row1, void* 
     TGS_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !attr_done[dev]) {
         TGS_CUDA(cudaFuncSetAttribute(k_bin_count, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (TGS_BIN_BAND_TILES + 1) * 4));
-        TGS_CUDA(cudaFuncSetAttribute(k_bin_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, kScatterWarps * (TGS_BIN_BAND_TILES * 4 + 8192 * 2)));   // rows of a very wide image + the hit lists
+        // one tile row of the widest image per warp + the hit lists
+        TGS_CUDA(cudaFuncSetAttribute(k_bin_scatter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TGS_BIN_SCATTER_MAX_TX * 4 + 8192 * 2));
+        TGS_CUDA(cudaFuncSetAttribute(k_bin_scatter<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (TGS_BIN_SCATTER_MAX_TX * 4) + 8192 * 2));
         attr_done[dev] = true;
     }
     {
@@ -476,14 +517,16 @@ int tgs_bin_scatter_pack(GeomView gv, BinView bv, int N, int64_t count, int64_t 
                          int row0, int row1, const void* temp, const uint2* ranges, const uint32_t* count_dev, cudaStream_t st) {
     if (count == 0 || N == 0 || row1 <= row0) return 0;
     const int T = Tx * Ty;
-    const Plan p = make_plan(N, Tx, row1 - row0);
+    const Plan p = make_plan(N, Tx, row1 - row0, row0 == 0 && row1 == Ty);
     const uint32_t* cnt = (const uint32_t*)temp;
     {
         TgsProfScope prof(TGS_STAGE_BIN_SCATTER, st);
-        const int nunits = p.nchunks * p.scatter.n;
-        const size_t per_warp = ((size_t)p.scatter.tiles + (size_t)(p.chunk + 1) / 2) * 4;
-        k_bin_scatter<<<(nunits + kScatterWarps - 1) / kScatterWarps, 32 * kScatterWarps, per_warp * kScatterWarps, st>>>(
-            N, p.chunk, p.scatter.n, nunits, gv.order, gv.span_sorted, Tx, row0, row1, p.scatter.rows, T, cnt, ranges,
+        const bool whole = (row0 == 0 && row1 == Ty);
+        const int ksub = whole ? 1 : 8;
+        const size_t smem = ((size_t)ksub * p.scatter.tiles + (size_t)(p.chunk + 1) / 2) * 4;
+        auto kern = whole ? k_bin_scatter<1> : k_bin_scatter<8>;
+        kern<<<p.nchunks * p.scatter.n, 32 * ksub, smem, st>>>(
+            N, p.chunk, p.scatter.n, gv.order, gv.span_sorted, Tx, row0, row1, p.scatter.rows, T, cnt, ranges,
             (uint32_t)(cap > 0xFFFFFFFFll ? 0xFFFFFFFFll : cap), bv.vals_sorted);
         tgs_count_own(1);
         TGS_CUDA(cudaGetLastError());

@@ -76,6 +76,7 @@ struct ImageView {
     uint32_t* count;         // [2] num_rendered (device copy), overflow flag
 };
 #define TGS_BIN_BAND_TILES 8192     /* tiles per band of the count kernel: 32 KB of shared-memory counters */
+#define TGS_BIN_SCATTER_MAX_TX 6144  /* widest image (in tiles) the scatter's shared memory holds: 8 cursor rows of 24 KB */
 #define TGS_BIN_SCATTER_TILES 256   /* tiles per band of the ordered scatter (one warp per (chunk, band)): measured best at c3 */
 GeomView tgs_geom_view(void* base, int N);
 BinView tgs_bin_view(void* base, int64_t I);
