@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TGS_ABI_VERSION 5
+#define TGS_ABI_VERSION 6
 
 #define TGS_EINVAL   (-1)   /* bad argument combination / shape */
 #define TGS_ENOMEM   (-2)   /* allocator callback returned NULL */
@@ -289,8 +289,8 @@ typedef struct TgsGeomLayout {
     size_t total;
 } TgsGeomLayout;
 typedef struct TgsBinningLayout {
-    size_t records;           /* TgsRecord[I], depth-sorted per tile, contiguous */
-    size_t vals_sorted;       /* uint32[I] Gaussian ids, final (tile, depth, id) order */
+    size_t vals_sorted;       /* uint32[I] Gaussian ids, final (tile, depth, id) order: each tile's list is one contiguous run
+                               * (the compositing kernels TMA-copy the ids and gather the per-Gaussian records by id) */
     size_t ckpt;              /* float[slots][5][256]: per-pixel (T, r, g, b, D) composited BEFORE list position
                                * ranges[tile].x + 256k, written by the forward for every 256-record boundary it crosses;
                                * slot = that position >> 8 (unique per boundary).  Lets the backward replay a tile's list

@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TGS_LIB_PATH") or os.path.join(HERE, "libtgs.so")   # override: A/B builds
 
-TGS_ABI_VERSION = 5
+TGS_ABI_VERSION = 6
 BUF_GEOM, BUF_BINNING, BUF_IMAGE, BUF_TEMP = 0, 1, 2, 3
 LOSS_NONE, LOSS_L1, LOSS_L2 = 0, 1, 2
 LOSS_MODES = {"none": LOSS_NONE, "l1": LOSS_L1, "l2": LOSS_L2}
@@ -66,7 +66,7 @@ class TgsGeomLayout(C.Structure):
 
 class TgsBinningLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in
-                ("records", "vals_sorted", "ckpt", "slot_tile", "ckpt_list", "work_counter", "slots", "total")]
+                ("vals_sorted", "ckpt", "slot_tile", "ckpt_list", "work_counter", "slots", "total")]
 
 
 class TgsImageLayout(C.Structure):

@@ -99,7 +99,6 @@ extern "C" int tgs_geom_layout(int32_t N, TgsGeomLayout* o) {
 }
 extern "C" int tgs_binning_layout(int64_t I, TgsBinningLayout* o) {
     Carver c; size_t n = (size_t)(I > 0 ? I : 0);
-    o->records = c.take(n * sizeof(TgsRecord));
     o->vals_sorted = c.take(n * sizeof(uint32_t));
     o->slots = (n >> 8) + 2;
     o->ckpt = c.take(o->slots * TGS_CKPT_FLOATS * sizeof(float));
@@ -137,7 +136,7 @@ GeomView tgs_geom_view(void* base, int N) {
 BinView tgs_bin_view(void* base, int64_t I) {
     TgsBinningLayout l; tgs_binning_layout(I, &l);
     char* b = (char*)base; BinView v;
-    v.records = (TgsRecord*)(b + l.records); v.vals_sorted = (uint32_t*)(b + l.vals_sorted);
+    v.vals_sorted = (uint32_t*)(b + l.vals_sorted);
     v.ckpt = (float*)(b + l.ckpt); v.slot_tile = (uint32_t*)(b + l.slot_tile);
     v.ckpt_list = (uint32_t*)(b + l.ckpt_list);
     v.work_counter = (uint32_t*)(b + l.work_counter);
@@ -236,7 +235,7 @@ extern "C" int tgs_forward(const TgsSettings* s, const TgsGaussians* g, tgs_allo
         BinView bv = tgs_bin_view(binning, capacity);
         int r = tgs_bin_scatter_pack(gv, bv, N, count, capacity, spec, cam.Tx, cam.Ty, cam.row0, cam.row1, temp, iv.ranges, iv.count, st); if (r) return r;
         if (s->debug) TGS_CUDA(cudaStreamSynchronize(st));
-        return tgs_launch_render_fwd(cam, s, bv, iv, capacity, out_color, out_depth, out_alpha, touch_target, residual_out, st);
+        return tgs_launch_render_fwd(cam, s, gv.records, bv, iv, capacity, out_color, out_depth, out_alpha, touch_target, residual_out, st);
     };
     auto read_count = [&]() -> int {                    // hp[0] = num_rendered, hp[1] = 32-bit overflow flag
         if (hp[1]) { tgs_set_error("num_rendered does not fit 32 bits (more than 4,294,967,295 tile instances)"); return TGS_EINVAL; }
@@ -288,7 +287,8 @@ extern "C" int tgs_backward_render(const TgsSettings* s, const TgsGaussians* g, 
     BinView bv = tgs_bin_view(saved->binning, saved->capacity > 0 ? saved->capacity : saved->num_rendered);
     ImageView iv = tgs_image_view(saved->image, cam.W, cam.H);
     if (g->N > 0) TGS_CUDA(cudaMemsetAsync(screen_grads, 0, sizeof(float) * TGS_NGRAD * (size_t)g->N, st));
-    return tgs_launch_render_bwd(cam, s, bv, iv, saved->num_rendered, dL_dcolor, dL_ddepth, dL_dalpha, touch, residual_out,
+    GeomView gvb = tgs_geom_view(saved->geom, g->N);
+    return tgs_launch_render_bwd(cam, s, gvb.records, bv, iv, saved->num_rendered, dL_dcolor, dL_ddepth, dL_dalpha, touch, residual_out,
                                  screen_grads, st);
 }
 

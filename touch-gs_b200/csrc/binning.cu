@@ -18,8 +18,8 @@
 //   3. k_bin_scatter: one WARP per chunk loads its row (+ the tile starts) into shared memory as per-tile cursors and
 //      walks its C Gaussians IN ORDER; the lanes take the tiles of the current Gaussian's rectangle, bump the cursors
 //      and write the Gaussian id to its final position.  Order inside a tile = order of the walk = depth order.
-//   4. k_pack: gather of the sorted 48-byte records -> shared memory -> one TMA bulk store per 256 records, so that
-//      every tile's list is one contiguous run the compositing kernels can stage with TMA bulk loads.
+// Every tile's list is then one contiguous run of ids; the compositing kernels (render.cu) TMA-copy the ids and gather
+// the 48-byte per-Gaussian records by id, so no per-instance copy of the records is ever written.
 // Tiles are processed in bands of tile rows (count: <= 8192 tiles = 32 KB of counters per CTA; scatter: ~1024 tiles
 // per single-warp unit) so any image size fits.
 //
@@ -402,49 +402,6 @@ k_bin_scatter(int N, int chunk, int nbands, const uint32_t* __restrict__ order, 
     }
 }
 
-// ---- 4. record packing.  256 instances per CTA: each thread gathers its instance's 48-byte record (3 x LDG.128;
-// the per-Gaussian record table is 48 MB at 1M splats and is kept L2-resident by evict_last loads while the
-// packed output streams through with an evict_first bulk store) into shared memory, and one thread writes the 12 KB
-// block back with a single TMA bulk store.
-__global__ void __launch_bounds__(256)
-k_pack(int64_t I_host, const uint32_t* __restrict__ I_dev, int64_t cap, const uint32_t* __restrict__ vals,
-       const float4* __restrict__ rec_in, float4* __restrict__ rec_out) {
-    __shared__ __align__(128) float4 sm[256 * 3];
-    // exact mode: I_host; speculative mode: the real count lives on the device, clamped to the buffer capacity
-    // (an overflowing speculation is discarded and re-run by the host)
-    int64_t I = I_host;
-    if (I_dev) { I = (int64_t)*I_dev; if (I > cap) I = cap; }
-    const int64_t j0 = (int64_t)blockIdx.x * 256;
-    if (j0 >= I) return;
-    const int64_t j = j0 + threadIdx.x;
-    if (j < I) {
-        uint32_t id;
-        asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(id) : "l"(vals + j));        // streamed once
-        const float4* src = rec_in + (size_t)3 * id;
-        float4 a, b, c;
-        uint64_t keep;
-        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
-        asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(src), "l"(keep));
-        asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(src + 1), "l"(keep));
-        asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(c.x), "=f"(c.y), "=f"(c.z), "=f"(c.w) : "l"(src + 2), "l"(keep));
-        sm[3 * threadIdx.x] = a; sm[3 * threadIdx.x + 1] = b; sm[3 * threadIdx.x + 2] = c;
-    }
-    // make the generic-proxy shared-memory writes visible to the async proxy, then bulk-store
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int64_t n = (I - j0) < 256 ? (I - j0) : 256;
-        const uint32_t bytes = (uint32_t)n * 48u;
-        uint64_t policy;
-        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(rec_out + 3 * j0),
-                     "r"((uint32_t)__cvta_generic_to_shared(sm)), "r"(bytes), "l"(policy)
-                     : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem may be released after the read
-    }
-}
-
 }  // namespace
 
 size_t tgs_depth_sort_temp_bytes(int N) {
@@ -511,8 +468,7 @@ int tgs_bin_count(GeomView gv, int N, int Tx, int Ty, int row0, int row1, void* 
     return 0;
 }
 
-// Phases 3-4.  `cap` = instances the binning buffer holds; `count` = instances to pack (== I in exact mode, == cap in
-// speculative mode, where the real count is read on the device from count_dev).
+// Phase 3.  `cap` = instances the binning buffer holds (speculative mode: positions beyond it are not written).
 int tgs_bin_scatter_pack(GeomView gv, BinView bv, int N, int64_t count, int64_t cap, bool speculative, int Tx, int Ty,
                          int row0, int row1, const void* temp, const uint2* ranges, const uint32_t* count_dev, cudaStream_t st) {
     if (count == 0 || N == 0 || row1 <= row0) return 0;
@@ -528,14 +484,6 @@ int tgs_bin_scatter_pack(GeomView gv, BinView bv, int N, int64_t count, int64_t 
         kern<<<p.nchunks * p.scatter.n, 32 * ksub, smem, st>>>(
             N, p.chunk, p.scatter.n, gv.order, gv.span_sorted, Tx, row0, row1, p.scatter.rows, T, cnt, ranges,
             (uint32_t)(cap > 0xFFFFFFFFll ? 0xFFFFFFFFll : cap), bv.vals_sorted);
-        tgs_count_own(1);
-        TGS_CUDA(cudaGetLastError());
-    }
-    {
-        TgsProfScope prof(TGS_STAGE_PACK, st);
-        k_pack<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(
-            count, speculative ? count_dev : nullptr, cap, bv.vals_sorted, reinterpret_cast<const float4*>(gv.records),
-            reinterpret_cast<float4*>(bv.records));
         tgs_count_own(1);
         TGS_CUDA(cudaGetLastError());
     }

@@ -67,6 +67,14 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                  : "memory");
 }
 
+// 16-byte asynchronous copy global -> shared (SASS: LDGSTS), grouped per thread
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 struct PixelMap {
     int px, py, pix; bool inside; float fx, fy;
     float x0, x1, y0, y1;           // pixel-centre rectangle of this warp's 8x4 patch
@@ -126,8 +134,22 @@ __device__ __forceinline__ bool patch_may_touch(const float4 a, const float4 q, 
 }
 
 // ------------------------------------------------------------------------------- forward
+// Staging of a tile's depth-sorted list.  The list is the contiguous run ids[rng.x .. rng.y) of Gaussian ids (binning.cu);
+// the 48-byte records live once per GAUSSIAN in the geometry buffer (48 MB at 1M splats: L2 resident).  Per batch of
+// 256 list entries:
+//   * one TMA bulk copy (cp.async.bulk + mbarrier complete_tx) brings the batch's 1 KB of ids into shared memory
+//     (3-deep ring, issued two batches ahead; the window is widened to 16-byte alignment);
+//   * every thread gathers ONE record by id with three 16-byte cp.async copies (LDGSTS) into the 2-stage record buffer,
+//     one batch ahead of the blend.
+// Only the batches a tile actually composites before all its pixels saturate are ever gathered (22 % of the instances at
+// c3), and no per-instance copy of the records is written to HBM at all (the packed-record array of the previous
+// design cost 96 B/instance of traffic and a kernel of its own: 0.175 ms at c3, 2.5 ms at c5).
+constexpr int kIdRing = 3;
+constexpr int kIdSlots = kBatch + 4;             // a 16-byte aligned window around 256 ids
+
 __global__ void __launch_bounds__(256)
-k_render_fwd(const uint2* __restrict__ ranges, uint32_t cap, const TgsRecord* __restrict__ recs, int W, int H, int Tx,
+k_render_fwd(const uint2* __restrict__ ranges, uint32_t cap, const uint32_t* __restrict__ ids,
+             const float4* __restrict__ table, int W, int H, int Tx,
              int row0, const float* __restrict__ bg, int normalize, float alpha_max, float* __restrict__ out_color,
              float* __restrict__ out_depth, float* __restrict__ out_alpha, float* __restrict__ final_T,
              uint32_t* __restrict__ n_contrib, float* __restrict__ depth_raw, float* __restrict__ color_acc,
@@ -135,7 +157,8 @@ k_render_fwd(const uint2* __restrict__ ranges, uint32_t cap, const TgsRecord* __
              uint32_t* __restrict__ ckpt_count,
              const float* __restrict__ t_target, float* __restrict__ residual) {
     __shared__ __align__(128) float4 sbuf[2][kBatch * 3];
-    __shared__ __align__(8) uint64_t full[2];
+    __shared__ __align__(16) uint32_t sid[kIdRing][kIdSlots];
+    __shared__ __align__(8) uint64_t idbar[kIdRing];
     const int tid = threadIdx.x, lane = tid & 31;
     const int tile = blockIdx.x + row0 * Tx;
     const PixelMap pm = map_pixel(tile, Tx, W, H);
@@ -145,23 +168,43 @@ k_render_fwd(const uint2* __restrict__ ranges, uint32_t cap, const TgsRecord* __
     rng.x = min(rng.x, cap); rng.y = min(rng.y, cap);
     const int len = (int)(rng.y - rng.x);
     const int nb = (len + kBatch - 1) / kBatch;
-    if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < kIdRing; ++k) mbar_init(&idbar[k], 1);
+        mbar_fence_init();
+    }
     __syncthreads();
-    const TgsRecord* src = recs + rng.x;
-    auto issue = [&](int b) {
-        int cnt = min(kBatch, len - b * kBatch);
-        uint32_t bytes = (uint32_t)cnt * kRecBytes;
-        mbar_expect_tx(&full[b & 1], bytes);
-        tma_bulk_g2s(sbuf[b & 1], src + (size_t)b * kBatch, bytes, &full[b & 1]);
+    // ids of batch b: TMA bulk copy of the 16-byte aligned window that contains list positions [p, p + cnt)
+    auto issue_ids = [&](int b) {
+        const uint32_t p = rng.x + (uint32_t)b * kBatch, pa = p & ~3u;
+        const uint32_t cnt = (uint32_t)min(kBatch, len - b * kBatch);
+        const uint32_t bytes = (((p - pa) + cnt) * 4u + 15u) & ~15u;
+        mbar_expect_tx(&idbar[b % kIdRing], bytes);
+        tma_bulk_g2s(sid[b % kIdRing], ids + pa, bytes, &idbar[b % kIdRing]);
     };
-    if (tid == 0) { if (nb > 0) issue(0); if (nb > 1) issue(1); }
+    // records of batch b: every thread gathers the record of ITS list entry
+    auto gather = [&](int b) {
+        mbar_wait(&idbar[b % kIdRing], (uint32_t)((b / kIdRing) & 1));
+        const uint32_t p = rng.x + (uint32_t)b * kBatch;
+        if (tid < min(kBatch, len - b * kBatch)) {
+            const uint32_t id = sid[b % kIdRing][(p & 3u) + tid];
+            const float4* src = table + (size_t)3 * id;
+            float4* dst = sbuf[b & 1] + 3 * tid;
+            cp_async16(dst, src); cp_async16(dst + 1, src + 1); cp_async16(dst + 2, src + 2);
+        }
+        cp_async_commit();
+    };
+    if (tid == 0) { for (int b = 0; b < kIdRing && b < nb; ++b) issue_ids(b); }
+    if (nb > 0) gather(0);
+    if (nb > 1) gather(1);
 
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, D = 0.f;
     uint32_t last = 0;
     bool done = !pm.inside;
     int b = 0;
     for (; b < nb; ++b) {
-        mbar_wait(&full[b & 1], (uint32_t)((b >> 1) & 1));
+        if (b + 1 < nb) cp_async_wait<1>(); else cp_async_wait<0>();    // this thread's copies of batch b have landed
+        __syncthreads();                                                  // ... and everybody else's
         const float4* s = sbuf[b & 1];
         const int cnt = min(kBatch, len - b * kBatch);
         for (int c0 = 0; c0 < cnt; c0 += 32) {
@@ -192,7 +235,8 @@ k_render_fwd(const uint2* __restrict__ ranges, uint32_t cap, const TgsRecord* __
         }
         const int nd = __syncthreads_count(done);
         if (nd == 256) break;
-        if (tid == 0 && b + 2 < nb) issue(b + 2);
+        if (tid == 0 && b + kIdRing < nb) issue_ids(b + kIdRing);        // its ring slot (batch b's ids) is free now
+        if (b + 2 < nb) gather(b + 2);                                    // into the record stage batch b just released
         if (b + 1 < nb) {
             // the list continues: CHECKPOINT the per-pixel state in front of list position (b+1)*256, so that the
             // backward can replay the tile's list in independent 256-record segments (one warp per segment)
@@ -202,9 +246,11 @@ k_render_fwd(const uint2* __restrict__ ranges, uint32_t cap, const TgsRecord* __
             if (tid == 0) { slot_tile[slot] = (uint32_t)tile; ckpt_list[atomicAdd(ckpt_count, 1u)] = slot; }
         }
     }
-    // a copy issued for batch b+1 may still be in flight if we broke out early: the CTA must not
-    // retire (and free its shared memory) before it lands.
-    if (tid == 0 && b < nb && b + 1 < nb) mbar_wait(&full[(b + 1) & 1], (uint32_t)(((b + 1) >> 1) & 1));
+    // copies may still be in flight if we broke out early: the CTA must not retire (and free its shared memory)
+    // before they land.  Records: this thread's groups; ids: batches issued but not yet waited for by gather().
+    cp_async_wait<0>();
+    // (broke out of iteration b: ids were issued through batch b + 2 and gather() waited through b + 1)
+    if (tid == 0 && b < nb && b + 2 < nb) mbar_wait(&idbar[(b + 2) % kIdRing], (uint32_t)(((b + 2) / kIdRing) & 1));
 
     if (pm.inside) {
         const size_t HW = (size_t)W * H;
@@ -282,7 +328,8 @@ constexpr int kPix = 4;
 constexpr int kSeg = 256;                       // == kBatch: the forward checkpoints once per staged batch
 
 __global__ void __launch_bounds__(kBwdThreads, 5)
-k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ recs, int W, int H, int Tx,
+k_render_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ ids, const float4* __restrict__ table,
+             int W, int H, int Tx,
              int row0, const float* __restrict__ bg, int normalize, float alpha_max, const float* __restrict__ final_T,
              const uint32_t* __restrict__ n_contrib, const float* __restrict__ depth_raw,
              const float* __restrict__ color_acc, const float* __restrict__ ckpt,
@@ -294,13 +341,8 @@ k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
              const float* __restrict__ t_gscale, int t_mode,
              int t_row0, int t_row1, float* __restrict__ residual, float* __restrict__ sgrad) {
     __shared__ __align__(128) float4 sbuf_all[kBwdWarps][2][kBwdBatch * 3];
-    __shared__ __align__(8) uint64_t full_all[kBwdWarps][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 (*sbuf)[kBwdBatch * 3] = sbuf_all[warp];
-    uint64_t* full = full_all[warp];
-    if (lane == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
-    __syncwarp();
-    uint32_t phase0 = 0, phase1 = 0;               // completed phases of the warp's two stage barriers
     const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
     // loss scale (mult / Z) times the upstream gradient of the touch-loss scalar (NULL = 1: the loss enters the
     // caller's objective with unit weight)
@@ -406,19 +448,45 @@ k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
         const int nb = (leff + kBwdBatch - 1) / kBwdBatch;
         if (nb <= 0) continue;
 
-        const TgsRecord* src = recs + rng.x + s0;
-        auto issue = [&](int q) {                       // sequence step q stages batch nb-1-q (back to front)
-            int b = nb - 1 - q;
-            int cnt = min(kBwdBatch, leff - b * kBwdBatch);
-            uint32_t bytes = (uint32_t)cnt * kRecBytes;
-            mbar_expect_tx(&full[q & 1], bytes);
-            tma_bulk_g2s(sbuf[q & 1], src + (size_t)b * kBwdBatch, bytes, &full[q & 1]);
+        // staging: the segment's records are gathered by Gaussian id from the per-Gaussian table (L2 resident), two per
+        // lane and batch, with 16-byte cp.async copies two batches ahead; the ids of the batch after that are prefetched
+        // into registers so that no gather waits for its ids
+        const uint32_t* seg_ids = ids + rng.x + s0;
+        auto load_ids = [&](int q, uint32_t& i0, uint32_t& i1) {      // sequence step q stages batch nb-1-q (back to front)
+            const int b = nb - 1 - q;
+            const int cnt = min(kBwdBatch, leff - b * kBwdBatch);
+            const uint32_t* p = seg_ids + b * kBwdBatch;
+            i0 = lane < cnt ? __ldg(p + lane) : 0u;
+            i1 = lane + 32 < cnt ? __ldg(p + lane + 32) : 0u;
         };
-        if (lane == 0) { issue(0); if (nb > 1) issue(1); }
+        auto gather = [&](int q, uint32_t i0, uint32_t i1) {
+            const int b = nb - 1 - q;
+            const int cnt = min(kBwdBatch, leff - b * kBwdBatch);
+            float4* dst = sbuf[q & 1];
+            if (lane < cnt) {
+                const float4* src = table + (size_t)3 * i0;
+                cp_async16(dst + 3 * lane, src); cp_async16(dst + 3 * lane + 1, src + 1); cp_async16(dst + 3 * lane + 2, src + 2);
+            }
+            if (lane + 32 < cnt) {
+                const float4* src = table + (size_t)3 * i1;
+                float4* d = dst + 3 * (lane + 32);
+                cp_async16(d, src); cp_async16(d + 1, src + 1); cp_async16(d + 2, src + 2);
+            }
+            cp_async_commit();
+        };
+        uint32_t n0 = 0, n1 = 0;
+        {
+            uint32_t a0, a1;
+            load_ids(0, a0, a1);
+            if (nb > 1) load_ids(1, n0, n1);
+            gather(0, a0, a1);
+            if (nb > 1) gather(1, n0, n1);
+            if (nb > 2) load_ids(2, n0, n1);
+        }
 
         for (int q = 0; q < nb; ++q) {
-            if (q & 1) { mbar_wait(&full[1], phase1 & 1u); ++phase1; }
-            else       { mbar_wait(&full[0], phase0 & 1u); ++phase0; }
+            if (q + 1 < nb) cp_async_wait<1>(); else cp_async_wait<0>();
+            __syncwarp();
             const int b = nb - 1 - q;
             const int cnt = min(kBwdBatch, leff - b * kBwdBatch);
             const float4* s = sbuf[q & 1];
@@ -487,7 +555,10 @@ k_render_bwd(const uint2* __restrict__ ranges, const TgsRecord* __restrict__ rec
                 }
             }
             __syncwarp();
-            if (lane == 0 && q + 2 < nb) issue(q + 2);
+            if (q + 2 < nb) {
+                gather(q + 2, n0, n1);
+                if (q + 3 < nb) load_ids(q + 3, n0, n1);
+            }
         }
     }
 }
@@ -542,14 +613,15 @@ int tgs_launch_touch_loss_value(const float* residual, const float* weight, int6
     return 0;
 }
 
-int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, BinView bv, ImageView iv, int64_t capacity,
-                          float* out_color, float* out_depth, float* out_alpha,
+int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, const TgsRecord* gv_records, BinView bv, ImageView iv,
+                          int64_t capacity, float* out_color, float* out_depth, float* out_alpha,
                           const float* touch_target, float* residual_out, cudaStream_t st) {
     int nt = cam.Tx * (cam.row1 - cam.row0);
     if (nt <= 0) return 0;
     TgsProfScope prof(TGS_STAGE_RENDER_FWD, st);
     TGS_CUDA(cudaMemsetAsync(bv.work_counter, 0, 2 * sizeof(uint32_t), st));
-    k_render_fwd<<<nt, 256, 0, st>>>(iv.ranges, (uint32_t)(capacity > 0xFFFFFFFFll ? 0xFFFFFFFFll : capacity), bv.records, cam.W, cam.H, cam.Tx, cam.row0, s->bg,
+    k_render_fwd<<<nt, 256, 0, st>>>(iv.ranges, (uint32_t)(capacity > 0xFFFFFFFFll ? 0xFFFFFFFFll : capacity), bv.vals_sorted,
+                                     reinterpret_cast<const float4*>(gv_records), cam.W, cam.H, cam.Tx, cam.row0, s->bg,
                                      s->depth_normalize, cam.alpha_max, out_color, out_depth, out_alpha, iv.final_T,
                                      iv.n_contrib, iv.depth_raw, iv.color_acc, bv.ckpt, bv.slot_tile, bv.ckpt_list,
                                      bv.work_counter + 1, touch_target, residual_out);
@@ -558,7 +630,8 @@ int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, BinView bv, I
     return 0;
 }
 
-int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, BinView bv, ImageView iv, int64_t num_rendered,
+int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, const TgsRecord* gv_records, BinView bv, ImageView iv,
+                          int64_t num_rendered,
                           const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
                           const TgsTouch* touch, float* residual, float* screen_grads, cudaStream_t st) {
     int nt = cam.Tx * (cam.row1 - cam.row0);
@@ -590,7 +663,7 @@ int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, BinView bv, I
     int64_t grid = (units + kBwdWarps - 1) / kBwdWarps;
     if (grid > (int64_t)cps * sms) grid = (int64_t)cps * sms;        // persistent: one resident wave
     TGS_CUDA(cudaMemsetAsync(bv.work_counter, 0, sizeof(uint32_t), st));
-    k_render_bwd<<<(unsigned)grid, kBwdThreads, 0, st>>>(iv.ranges, bv.records, cam.W, cam.H, cam.Tx, cam.row0, s->bg,
+    k_render_bwd<<<(unsigned)grid, kBwdThreads, 0, st>>>(iv.ranges, bv.vals_sorted, reinterpret_cast<const float4*>(gv_records), cam.W, cam.H, cam.Tx, cam.row0, s->bg,
                                      s->depth_normalize, cam.alpha_max, iv.final_T, iv.n_contrib, iv.depth_raw,
                                      iv.color_acc, bv.ckpt, bv.slot_tile, bv.ckpt_list, bv.work_counter, 2 * nt, dL_dcolor,
                                      dL_ddepth, dL_dalpha, tt, tw, ts, tg, mode, tr0, tr1, residual, screen_grads);

@@ -178,7 +178,7 @@ extern "C" int tgs_rasterize_screen_forward(const TgsSettings* s, int32_t N, con
     rc = tgs_bin_scatter_pack(gv, bv, N, I, I, false, cam.Tx, cam.Ty, cam.row0, cam.row1, temp, iv.ranges, iv.count, st); if (rc) return rc;
     TgsSettings s2 = *s;
     s2.depth_normalize = 0;
-    rc = tgs_launch_render_fwd(cam, &s2, bv, iv, I, out_color, out_depth, out_alpha, nullptr, nullptr, st); if (rc) return rc;
+    rc = tgs_launch_render_fwd(cam, &s2, gv.records, bv, iv, I, out_color, out_depth, out_alpha, nullptr, nullptr, st); if (rc) return rc;
     saved->geom = geom; saved->binning = binning; saved->image = image; saved->num_rendered = I; saved->capacity = I;
     return 0;
 }
@@ -195,7 +195,9 @@ extern "C" int tgs_rasterize_screen_backward(const TgsSettings* s, int32_t N, co
     if (N > 0) TGS_CUDA(cudaMemsetAsync(screen_grads, 0, sizeof(float) * TGS_NGRAD * (size_t)N, st));
     TgsSettings s2 = *s;
     s2.depth_normalize = 0;
-    return tgs_launch_render_bwd(cam, &s2, bv, iv, saved->num_rendered, dL_dcolor, dL_ddepth, dL_dalpha, nullptr, nullptr,
+    if (!saved->geom) { tgs_set_error("tgs_rasterize_screen_backward: saved geometry missing"); return TGS_ESTATE; }
+    GeomView gvb = tgs_geom_view(saved->geom, N);
+    return tgs_launch_render_bwd(cam, &s2, gvb.records, bv, iv, saved->num_rendered, dL_dcolor, dL_ddepth, dL_dalpha, nullptr, nullptr,
                                  screen_grads, st);
 }
 

@@ -8,9 +8,8 @@
 #include "tgs_math.cuh"
 
 // ---------------------------------------------------------------------------------- records
-// One 48-byte record per Gaussian (geometry buffer) and, after the sort, one per tile instance
-// (binning buffer) so that every tile's depth-sorted list is CONTIGUOUS in HBM and can be moved
-// into shared memory by a single TMA bulk copy (cp.async.bulk) per batch.
+// One 48-byte record per Gaussian (geometry buffer).  The compositing kernels stage a tile's depth-sorted list by
+// TMA-copying its contiguous run of Gaussian ids and gathering these records by id (render.cu).
 //   a = (x_pix, y_pix, depth, bits(gaussian id))
 //   b = (conic A, conic B, conic C, opacity)
 //   c = (r, g, b, thr)   thr = -ln(255*opacity): power threshold of the alpha >= 1/255 test
@@ -61,8 +60,7 @@ struct GeomView {
     void* temp; size_t temp_bytes;
 };
 struct BinView {
-    uint32_t* vals_sorted;   // [I] Gaussian ids in final (tile, depth, id) order
-    TgsRecord* records;      // [I] packed, sorted
+    uint32_t* vals_sorted;   // [I] Gaussian ids in final (tile, depth, id) order: every tile's list is one contiguous run
     float* ckpt;             // [slots][5][256] forward checkpoints at 256-record boundaries of the tile lists
     uint32_t* slot_tile;     // [slots] owning tile of the boundary in a slot (valid for the slots in ckpt_list)
     uint32_t* ckpt_list;     // [slots] slots the forward checkpointed, in completion order
@@ -104,10 +102,11 @@ int tgs_bin_count(GeomView gv, int N, int Tx, int Ty, int row0, int row1, void* 
 int tgs_bin_scatter_pack(GeomView gv, BinView bv, int N, int64_t count, int64_t cap, bool speculative, int Tx, int Ty,
                          int row0, int row1, const void* temp, const uint2* ranges, const uint32_t* count_dev, cudaStream_t st);
 // render.cu
-int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, BinView bv, ImageView iv, int64_t capacity,
-                          float* out_color, float* out_depth, float* out_alpha,
+int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, const TgsRecord* gv_records, BinView bv, ImageView iv,
+                          int64_t capacity, float* out_color, float* out_depth, float* out_alpha,
                           const float* touch_target, float* residual_out, cudaStream_t st);
-int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, BinView bv, ImageView iv, int64_t num_rendered,
+int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, const TgsRecord* gv_records, BinView bv, ImageView iv,
+                          int64_t num_rendered,
                           const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
                           const TgsTouch* touch, float* residual, float* screen_grads, cudaStream_t st);
 int tgs_launch_loss_scale(const float* target, int64_t P, float mult, float norm, float* out, cudaStream_t st);

@@ -63,7 +63,6 @@ def forward_state(means3D, opacities, rs: GaussianRasterizationSettings, shs=Non
         vals=_view(binning, bl.vals_sorted, I, torch.int32),
         ranges=_view(image, il.ranges, Tx * Ty * 2, torch.int32).view(Tx * Ty, 2),
         num_rendered_device=int(_view(image, il.count, 2, torch.int32)[0].item()) & 0xFFFFFFFF,
-        records=_view(binning, bl.records, I * 12, torch.float32).view(I, 12),
         final_T=_view(image, il.final_T, H * W, torch.float32).view(H, W),
         n_contrib=_view(image, il.n_contrib, H * W, torch.int32).view(H, W),
         depth_raw=_view(image, il.depth_raw, H * W, torch.float32).view(H, W),
@@ -81,6 +80,9 @@ def forward_state(means3D, opacities, rs: GaussianRasterizationSettings, shs=Non
         if ok:
             tid = tile_of_range
     out["tile_ids"] = tid
+    # no per-instance copy of the records exists any more (the compositing kernels gather them by id): the view a test
+    # may want is simply the per-Gaussian table indexed by the sorted ids
+    out["records"] = rec[out["vals"].long()]
     # the spec'd 64-bit sort key of every sorted instance: tile << 32 | bits(depth of its Gaussian)
     dbits = out["gdepth"].contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
     out["keys"] = (out["tile_ids"] << 32) | dbits[out["vals"].long()]
