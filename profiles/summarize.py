@@ -38,7 +38,7 @@ if os.path.exists(path):
         a[1] += v
     tot = sum(a[1] for a in agg.values())
     w(f"# {tag}: ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache serialised: compare SHARES)")
-    w("command: python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --cameras 1   (first 400 launches; every launch is camera 0)")
+    w("command: python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-refcuda --cameras 1   (first 400 launches; every launch is camera 0)")
     w()
     w("| kernel | launches | total us | share |")
     w("|---|---:|---:|---:|")
@@ -77,9 +77,18 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum",
         "l1tex__t_requests_pipe_lsu_mem_global_op_red.sum", "lts__t_sectors_op_red.sum",
-        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__inst_executed_pipe_xu.sum"]
-for kern in ("render_bwd", "render_fwd", "preprocess_bwd", "pack", "duplicate", "preprocess", "sort", "adam", "ssim_fwd",
-             "ssim_bwd", "ref_render_bwd"):
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__inst_executed_pipe_xu.sum",
+        "smsp__warps_active.avg.per_cycle_active", "smsp__warps_eligible.avg.per_cycle_active", "lts__t_sector_hit_rate.pct",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio"]
+for kern in ("render_bwd", "render_fwd", "bin_scatter", "bin_count", "bin_prefix", "preprocess_bwd", "pack", "duplicate",
+             "preprocess", "sort", "adam", "ssim_fwd", "ssim_bwd", "ref_render_bwd", "preprocess_bwd_gather"):
     rep = os.path.join(G, f"{tag}_{kern}.ncu-rep")
     if not os.path.exists(rep):
         continue

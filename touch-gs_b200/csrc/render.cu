@@ -159,6 +159,7 @@ k_render_fwd(const uint2* __restrict__ ranges, uint32_t cap, const uint32_t* __r
     __shared__ __align__(128) float4 sbuf[2][kBatch * 3];
     __shared__ __align__(16) uint32_t sid[kIdRing][kIdSlots];
     __shared__ __align__(8) uint64_t idbar[kIdRing];
+    __shared__ __align__(8) uint64_t full[2];        // record stages: 256 arrivals, one per thread when its copies land
     const int tid = threadIdx.x, lane = tid & 31;
     const int tile = blockIdx.x + row0 * Tx;
     const PixelMap pm = map_pixel(tile, Tx, W, H);
@@ -171,6 +172,7 @@ k_render_fwd(const uint2* __restrict__ ranges, uint32_t cap, const uint32_t* __r
     if (tid == 0) {
 #pragma unroll
         for (int k = 0; k < kIdRing; ++k) mbar_init(&idbar[k], 1);
+        mbar_init(&full[0], 256); mbar_init(&full[1], 256);
         mbar_fence_init();
     }
     __syncthreads();
@@ -192,7 +194,8 @@ k_render_fwd(const uint2* __restrict__ ranges, uint32_t cap, const uint32_t* __r
             float4* dst = sbuf[b & 1] + 3 * tid;
             cp_async16(dst, src); cp_async16(dst + 1, src + 1); cp_async16(dst + 2, src + 2);
         }
-        cp_async_commit();
+        // arrive on the stage's mbarrier when THIS thread's copies have landed (immediately if it issued none)
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[b & 1])) : "memory");
     };
     if (tid == 0) { for (int b = 0; b < kIdRing && b < nb; ++b) issue_ids(b); }
     if (nb > 0) gather(0);
@@ -203,8 +206,7 @@ k_render_fwd(const uint2* __restrict__ ranges, uint32_t cap, const uint32_t* __r
     bool done = !pm.inside;
     int b = 0;
     for (; b < nb; ++b) {
-        if (b + 1 < nb) cp_async_wait<1>(); else cp_async_wait<0>();    // this thread's copies of batch b have landed
-        __syncthreads();                                                  // ... and everybody else's
+        mbar_wait(&full[b & 1], (uint32_t)((b >> 1) & 1));               // all 256 threads' copies of batch b have landed
         const float4* s = sbuf[b & 1];
         const int cnt = min(kBatch, len - b * kBatch);
         for (int c0 = 0; c0 < cnt; c0 += 32) {
@@ -247,8 +249,8 @@ k_render_fwd(const uint2* __restrict__ ranges, uint32_t cap, const uint32_t* __r
         }
     }
     // copies may still be in flight if we broke out early: the CTA must not retire (and free its shared memory)
-    // before they land.  Records: this thread's groups; ids: batches issued but not yet waited for by gather().
-    cp_async_wait<0>();
+    // before they land.  Records: this thread's cp.async copies; ids: batches issued but not yet waited for by gather().
+    asm volatile("cp.async.wait_all;" ::: "memory");
     // (broke out of iteration b: ids were issued through batch b + 2 and gather() waited through b + 1)
     if (tid == 0 && b < nb && b + 2 < nb) mbar_wait(&idbar[(b + 2) % kIdRing], (uint32_t)(((b + 2) / kIdRing) & 1));
 
