@@ -166,36 +166,55 @@ k_ssim_bwd(const float* __restrict__ color, const float* __restrict__ gt, const 
 }
 
 // lambda_dssim == 0: the loss is the plain L1 mean -- two streaming passes (sum, then sign), 16-byte accesses.
+// Plain L1 (lambda_dssim = 0): HBM-bound streaming kernels.  blockIdx.y = channel; a channel's loss rows are one
+// contiguous run of floats, read with 16-byte loads when the run is 16-byte aligned (scalar otherwise): no per-element
+// integer division, 8 floats in flight per thread.
 __global__ void __launch_bounds__(256)
 k_l1_fwd(const float* __restrict__ color, const float* __restrict__ gt, int W, int H, int y_begin, int y_end,
          double* __restrict__ sums) {
     __shared__ float red[8];
-    const int64_t row_elems = (int64_t)W * (y_end - y_begin);
-    const int64_t n = 3 * row_elems, stride = (int64_t)gridDim.x * blockDim.x;
-    const size_t HW = (size_t)W * H;
+    const size_t base = (size_t)blockIdx.y * W * H + (size_t)y_begin * W;
+    const int64_t n = (int64_t)W * (y_end - y_begin);
+    const float* c = color + base;
+    const float* g = gt + base;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float acc = 0.0f;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int ch = (int)(i / row_elems);
-        const size_t o = ch * HW + (size_t)y_begin * W + (size_t)(i - ch * row_elems);
-        acc += fabsf(color[o] - gt[o]);
+    if ((((uintptr_t)c | (uintptr_t)g) & 15) == 0 && (n & 3) == 0) {
+        const float4* c4 = reinterpret_cast<const float4*>(c);
+        const float4* g4 = reinterpret_cast<const float4*>(g);
+        for (int64_t i = t0; i < (n >> 2); i += stride) {
+            const float4 a = __ldcs(c4 + i), b = __ldcs(g4 + i);
+            acc += (fabsf(a.x - b.x) + fabsf(a.y - b.y)) + (fabsf(a.z - b.z) + fabsf(a.w - b.w));
+        }
+    } else {
+        for (int64_t i = t0; i < n; i += stride) acc += fabsf(c[i] - g[i]);
     }
     const float b = block_sum_256(acc, red);
     if (threadIdx.x == 0) atomicAdd(sums, (double)b);
 }
+
+// dcolor rows [o_begin, o_end) <- g * sign(color - gt) on the loss rows [y_begin, y_end), 0 on the other rows written
 __global__ void __launch_bounds__(256)
 k_l1_bwd(const float* __restrict__ color, const float* __restrict__ gt, int W, int H, int y_begin, int y_end,
          int o_begin, int o_end, float inv_n, const float* __restrict__ grad_out, float* __restrict__ dcolor) {
-    const int64_t row_elems = (int64_t)W * (o_end - o_begin);
-    const int64_t n = 3 * row_elems, stride = (int64_t)gridDim.x * blockDim.x;
-    const size_t HW = (size_t)W * H;
+    const size_t base = (size_t)blockIdx.y * W * H + (size_t)o_begin * W;
+    const int64_t n = (int64_t)W * (o_end - o_begin);
+    // loss rows as a range of the run's element indices
+    const int64_t l0 = (int64_t)W * (max(y_begin, o_begin) - o_begin), l1 = (int64_t)W * (min(y_end, o_end) - o_begin);
     const float g = (grad_out ? grad_out[0] : 1.0f) * inv_n;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int ch = (int)(i / row_elems);
-        const int64_t r = i - ch * row_elems;
-        const size_t o = ch * HW + (size_t)o_begin * W + (size_t)r;
-        const int py = o_begin + (int)(r / W);
-        const float x = color[o], y = gt[o];
-        dcolor[o] = (py >= y_begin && py < y_end) ? g * (float)((x > y) - (x < y)) : 0.0f;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    auto sgn = [&](float x, float y, int64_t e) { return (e >= l0 && e < l1) ? g * (float)((x > y) - (x < y)) : 0.0f; };
+    if ((((uintptr_t)(color + base) | (uintptr_t)(gt + base) | (uintptr_t)(dcolor + base)) & 15) == 0 && (n & 3) == 0) {
+        const float4* c4 = reinterpret_cast<const float4*>(color + base);
+        const float4* g4 = reinterpret_cast<const float4*>(gt + base);
+        float4* d4 = reinterpret_cast<float4*>(dcolor + base);
+        for (int64_t i = t0; i < (n >> 2); i += stride) {
+            const float4 a = __ldcs(c4 + i), b = __ldcs(g4 + i);
+            const int64_t e = i << 2;
+            d4[i] = make_float4(sgn(a.x, b.x, e), sgn(a.y, b.y, e + 1), sgn(a.z, b.z, e + 2), sgn(a.w, b.w, e + 3));
+        }
+    } else {
+        for (int64_t i = t0; i < n; i += stride) dcolor[base + i] = sgn(color[base + i], gt[base + i], i);
     }
 }
 
@@ -404,10 +423,11 @@ extern "C" int tgs_photometric_loss_forward(const float* color, const float* gt,
     TGS_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(double), st));
     dim3 grid((W + kST - 1) / kST, (row_end - row_begin + kST - 1) / kST, 3);
     if (lambda_dssim == 0.0f) {                     // plain L1: no SSIM pass, no derivative maps
-        const int64_t n = 3ll * W * (row_end - row_begin);
+        const int64_t n = 1ll * W * (row_end - row_begin);         // per channel
         int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
-        if (blocks > 148 * 8) blocks = 148 * 8;
-        k_l1_fwd<<<(unsigned)blocks, 256, 0, st>>>(color, gt, W, H, row_begin, row_end, sums);
+        if (blocks > 148 * 4) blocks = 148 * 4;
+        if (blocks < 1) blocks = 1;
+        k_l1_fwd<<<dim3((unsigned)blocks, 3), 256, 0, st>>>(color, gt, W, H, row_begin, row_end, sums);
     } else
     k_ssim_fwd<<<grid, 256, 0, st>>>(color, gt, W, H, row_begin, row_end, taps, dmaps, sums);
     k_loss_finish<<<1, 1, 0, st>>>(sums, 3.0 * W * (double)(row_end - row_begin), 3.0 * W * (double)H, lambda_dssim, loss_out);
@@ -428,10 +448,11 @@ extern "C" int tgs_photometric_loss_backward(const float* color, const float* gt
     dim3 grid((W + kST - 1) / kST, (out_row_end - out_row_begin + kST - 1) / kST, 3);
     TgsProfScope prof(TGS_STAGE_PHOTO_BWD, st);
     if (lambda_dssim == 0.0f) {
-        const int64_t n = 3ll * W * (out_row_end - out_row_begin);
+        const int64_t n = 1ll * W * (out_row_end - out_row_begin);  // per channel
         int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
-        if (blocks > 148 * 8) blocks = 148 * 8;
-        k_l1_bwd<<<(unsigned)blocks, 256, 0, st>>>(color, gt, W, H, row_begin, row_end, out_row_begin, out_row_end,
+        if (blocks > 148 * 4) blocks = 148 * 4;
+        if (blocks < 1) blocks = 1;
+        k_l1_bwd<<<dim3((unsigned)blocks, 3), 256, 0, st>>>(color, gt, W, H, row_begin, row_end, out_row_begin, out_row_end,
                                                    (float)(1.0 / (3.0 * W * (double)H)), grad_out, dL_dcolor);
     } else
     k_ssim_bwd<<<grid, 256, 0, st>>>(color, gt, dmaps, W, H, row_begin, row_end, out_row_begin, out_row_end, taps,
