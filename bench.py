@@ -9,7 +9,9 @@ A "step" = one forward + backward of the operator for one camera of the workload
 preprocess -> bin + sort -> per-tile compositing of RGB + expected depth -> backward with the touch
 depth-L1 gradient fused in -> preprocess backward.  Workload = BASELINE config c3: 1M synthetic
 Gaussians, 1920x1080, SH degree 3, fused tactile depth-L1.  With N > 1 ranks the image
-is sharded by tile rows and the [N,10] screen-space gradients are all-reduced once per step (NCCL).
+is sharded by tile rows (bands balanced by measured instance counts) and the [N,10] screen-space gradients are
+exchanged once per step: by default a P2P gather over NVLink fused into the preprocess-backward kernel
+(--exchange p2p), or one NCCL all-reduce (--exchange nccl).
 
 Prints ONE JSON line (rank 0).  See DESIGN.md §6 for the meaning of every key.
 """

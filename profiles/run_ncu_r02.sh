@@ -13,6 +13,6 @@ cap render_fwd k_render_fwd 6
 cap bin_scatter k_bin_scatter 6
 cap bin_count k_bin_count 6
 cap bin_prefix k_bin_prefix 6
-cap preprocess "k_preprocess<" 6
+cap preprocess "k_preprocess$" 6
 cap preprocess_bwd k_preprocess_bwd 4
 ls -la gpurun_out/ | grep ${TAG}

@@ -40,7 +40,9 @@ class GaussianRasterizationSettings(NamedTuple):
     projmatrix: torch.Tensor      # [4,4] transposed full projection
     sh_degree: int
     campos: torch.Tensor
-    prefiltered: bool = False
+    prefiltered: bool = False     # accepted for signature parity: the reference-era kernels only use it to ASSERT that a
+                                  # caller who pre-culled with markVisible passes no point behind the near plane; results
+                                  # never depend on it, and here a culled point is simply skipped
     debug: bool = False
 
 
