@@ -62,6 +62,8 @@ def parse():
                     help="multi-GPU exchange of the [N,10] screen gradients: p2p = gather fused into the preprocess-backward "
                          "kernel over peer-mapped memory (NVLink); nccl = one all-reduce (also the fallback if p2p is unavailable)")
     ap.add_argument("--no-hints", action="store_true", help="synchronous sizing in every forward (no rendered_hint)")
+    ap.add_argument("--defer-count", default="auto", choices=["auto", "on", "off"],
+                    help="operator option defer_count (with the per-view hints): auto = on for N > 1")
     ap.add_argument("--even-bands", action="store_true", help="N > 1: equal tile-row bands instead of bands balanced by instance count")
     ap.add_argument("--no-measured-configs", action="store_true",
                     help="--impl reference: skip the full CPU runs of configs c1 / c2 (about a minute on 8 cores)")
@@ -199,12 +201,14 @@ class Stepper:
         self.band, self.group = band, group
         self.peer = None
         self.use_hints = True
+        self.defer_count = False
         H = cfg["H"]
         self.y0, self.y1 = (0, H) if band is None else T.sharding.band_pixel_rows(band, H)
         self.inv = 1.0 / (3.0 * cfg["H"] * cfg["W"])
         # persistent device staging buffers for the end-to-end path
         self.stage = None
         self.hints = {}          # per training view: instance count of its previous render (+5 %), see _run
+        self.rasterizers = {}
 
     def _run(self, cam, view, proj, campos, gt, target, weight):
         """`rendered_hint`: a trainer revisits the same views every epoch, so it passes the view's previous
@@ -213,23 +217,29 @@ class Stepper:
         binning exactly if the hint was too small)."""
         T, cfg, p = self.T, self.cfg, self.p
         key = id(cam)
-        rs = T.GaussianRasterizationSettings(cfg["H"], cfg["W"], cam.tanfovx, cam.tanfovy, self.bg, 1.0, view, proj,
-                                             cfg["sh_degree"], campos, False, False)
+        # the rasterizer module of a view is built once (a trainer keeps one per camera): the settings only hold
+        # references to the camera tensors, whose CONTENTS the end-to-end path refreshes in place every step
+        rkey = (key, view.data_ptr())
+        ras = self.rasterizers.get(rkey)
+        if ras is None:
+            rs = T.GaussianRasterizationSettings(cfg["H"], cfg["W"], cam.tanfovx, cam.tanfovy, self.bg, 1.0, view, proj,
+                                                 cfg["sh_degree"], campos, False, False)
+            ras = self.rasterizers[rkey] = T.GaussianRasterizer(rs)
         for v in p.values():
             v.grad = None
-        ras = T.GaussianRasterizer(rs)
         color, radii, depth, alpha, resid = ras(
             p["means3D"], None, p["opacities"], shs=p["shs"], scales=p["scales"], rotations=p["rotations"],
             touch_depth=target, touch_weight=weight, depth_loss="l1", depth_loss_mult=DEPTH_LOSS_MULT,
             depth_normalize=True, tile_rows=self.band, process_group=self.group, peer_exchange=self.peer,
-            rendered_hint=self.hints.get(key, 0) if self.use_hints else 0)
-        self.hints[key] = int(ras.last_num_rendered * 1.05) + 4096
+            rendered_hint=self.hints.get(key, 0) if self.use_hints else 0, defer_count=self.defer_count)
         y0, y1 = self.y0, self.y1
         # mean |C - C*| (band-local part) through the library's fused photometric loss (lambda_dssim = 0: plain L1,
         # one kernel forward, one backward)
         rows = None if self.band is None else (y0, y1)
         loss = T.photometric_loss(color, gt, 0.0, rows, rows)
         loss.backward()
+        # (read after backward: with a deferred count the number is a ticket that backward has redeemed by now)
+        self.hints[key] = int(ras.last_num_rendered * 1.05) + 4096
         return loss
 
     def forward_only_step(self, b):
@@ -628,6 +638,9 @@ def main():
     else:
         stepper = Stepper(cfg, params, bg, dev, band, group)
     stepper.use_hints = not args.no_hints
+    # deferred count: the forward never waits for num_rendered (checked when backward runs).  On by default for N > 1, where
+    # a rank's GPU work per step is comparable to the host path and the forward's wait would leave the GPU idle
+    stepper.defer_count = stepper.use_hints and (args.defer_count == "on" or (args.defer_count == "auto" and world > 1)) and not train_mode
     stepper.forward_only = bool(args.forward_only) and not train_mode
     if stepper.forward_only:
         args.no_e2e = args.no_refcuda = args.no_cpu_baseline = True
@@ -849,7 +862,8 @@ def main():
                    "num_rendered_cam0": I_cam0, "visible_cam0": n_vis,
                    "parallelism": "single GPU" if world == 1 else f"tile-row shard x{world}; [N,10] fp32 screen-gradient exchange: {exchange}",
                    "bands": None if bands_all is None else {"policy": band_policy, "tile_rows": [list(b) for b in bands_all]},
-                   "rendered_hint": "off (synchronous sizing)" if args.no_hints else "per-view instance count of the previous visit +5% (speculative sizing; exact re-run on overflow)",
+                   "rendered_hint": "off (synchronous sizing)" if args.no_hints else ("per-view instance count of the previous visit +5% (speculative sizing; "
+                                    + ("count deferred: checked when backward runs, an overflow would raise)" if stepper.defer_count else "exact re-run on overflow)")),
                    "l2_policy": "working set per step (params+grads 472 MB, instance records >250 MB) exceeds the 126 MB L2; no explicit flush"},
         "clocks": clocks,
         "gpu_launches": own + cub,

@@ -29,11 +29,12 @@
 extern "C" {
 #endif
 
-#define TGS_ABI_VERSION 6
+#define TGS_ABI_VERSION 7
 
 #define TGS_EINVAL   (-1)   /* bad argument combination / shape */
 #define TGS_ENOMEM   (-2)   /* allocator callback returned NULL */
 #define TGS_ESTATE   (-3)   /* saved buffers do not match the call */
+#define TGS_EOVERFLOW (-4)  /* a deferred speculative forward rendered more instances than its buffers held */
 
 /* which scratch buffer an allocation is for (the three opaque byte buffers of SURVEY §8b) */
 #define TGS_BUF_GEOM    0   /* per-Gaussian state, lives fwd -> bwd */
@@ -63,7 +64,13 @@ typedef struct TgsSettings {
     int32_t tile_row_begin;   /* tile-row band rendered by this rank (multi-GPU shard) */
     int32_t tile_row_end;     /* exclusive; (0, ceil(H/16)) = whole image; (0,0) is also whole image */
     int32_t depth_normalize;  /* 1: returned depth = D/alpha (expected depth), 0: raw sum */
-    int32_t reserved0;
+    int32_t defer_count;      /* with rendered_hint > 0: do NOT wait for num_rendered in tgs_forward at all.  saved->num_rendered
+                               * is then a negative TICKET; tgs_backward_render (or tgs_forward_resolve) redeems it once the count
+                               * has long arrived.  If the count exceeded the hint the forward's outputs were computed from a
+                               * truncated list: the redeeming call returns TGS_EOVERFLOW and the caller must redo the step with
+                               * a larger hint (a trainer's hint = the view's previous count + a margin never overflows in steady
+                               * state).  Keeps the host a full step ahead of the GPU: what a tile-row shard with little work per
+                               * rank needs. */
     int64_t rendered_hint;    /* 0: synchronous sizing (read num_rendered, then bin).  > 0: SPECULATIVE mode: the
                                * binning buffers are sized for this many instances and the binning + render kernels
                                * are enqueued BEFORE the host waits for the real count (the wait is on an event
@@ -155,6 +162,10 @@ void        tgs_launch_counts(uint64_t* own, uint64_t* cub);
 #define TGS_NUM_STAGES            15
 int tgs_profile_enable(int32_t on);
 int tgs_profile_read(float* ms_per_stage, int32_t* launches_per_stage);
+
+/* Redeem the ticket a deferred forward left in saved->num_rendered (see TgsSettings.defer_count): waits for the count's
+ * event (normally long complete), returns the instance count.  Idempotent until the ticket slot is reused (8 forwards later). */
+int tgs_forward_resolve(int64_t ticket, int64_t capacity, int64_t* num_rendered_out);
 
 /* replaces markVisible: present[i] = view-space z > 0.2 */
 int tgs_mark_visible(int32_t N, const float* means3D, const float* viewmatrix,

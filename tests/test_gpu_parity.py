@@ -364,6 +364,40 @@ def test_golden_fixture():
         assert_close_tensor(got[k], torch.from_numpy(z["grad_" + k]), "grad_" + k, 1e-4)
 
 
+def test_deferred_count_is_identical_and_overflow_raises_in_backward():
+    """defer_count: the forward never waits for num_rendered; with a sufficient hint nothing changes, with a hint that
+    is too small the backward refuses to run on the truncated forward."""
+    c, sc, cam = _case("ragged")
+    rs = cuda_settings(cam, c["deg"], DEV, (0.1, 0.2, 0.3), c.get("mod", 1.0))
+    m, s, r, o, sh = _to(DEV, sc.means3D, sc.scales, sc.rotations, sc.opacities, sc.shs)
+    H, W = c["H"], c["W"]
+    g = torch.Generator().manual_seed(2)
+    grgb = (torch.rand(3, H, W, generator=g) / (3 * H * W)).to(DEV)
+
+    def run(**kw):
+        mm = m.clone().requires_grad_(True)
+        ras = T.GaussianRasterizer(rs)
+        out = ras(mm, None, o, shs=sh, scales=s, rotations=r, **kw)
+        (out[0] * grgb).sum().backward()
+        return out, mm.grad, ras
+    ref, gref, ras0 = run()
+    I = ras0.last_num_rendered
+    for binding in ("ext", "ctypes"):
+        T._lib.use_binding(binding)
+        try:
+            out, grad, ras = run(rendered_hint=int(I * 1.2), defer_count=True)
+            for a, b in zip(out[:5], ref[:5]):
+                assert torch.equal(a, b)
+            assert rel_inf(grad, gref) < 1e-5
+            assert ras.last_num_rendered == I                      # the ticket is redeemed on access
+            with pytest.raises(Exception, match="overflowed"):
+                run(rendered_hint=max(1, int(I * 0.3)), defer_count=True)
+            out2, grad2, _ = run(rendered_hint=int(I * 0.3))         # without defer_count: exact re-run, same result
+            assert torch.equal(out2[0], ref[0]) and rel_inf(grad2, gref) < 1e-5
+        finally:
+            T._lib.use_binding("ext")
+
+
 # ----------------------------------------------------------------------------- edge cases
 def test_empty_input():
     cam = synth.look_at_camera(64, 48, (0, 0, -3.0))

@@ -38,7 +38,7 @@ def test_torch_check_errors_without_gpu(ext):
         ext.mark_visible(z(4, 2), torch.eye(4), torch.eye(4))
     with pytest.raises(RuntimeError, match="CUDA-only"):
         ext.rasterize_gaussians(z(3), z(4, 3), e, z(4), z(4, 3), z(4, 4), 1.0, e, torch.eye(4), torch.eye(4), 0.5, 0.5, 64, 64,
-                                z(4, 1, 3), 0, z(3), False, False, 0, 4, True, 0, None)
+                                z(4, 1, 3), 0, z(3), False, False, 0, 4, True, 0, None, False)
 
 
 @pytest.mark.gpu
@@ -52,7 +52,7 @@ def test_torch_check_errors_on_device(ext):
     def call(**kw):
         a = dict(base, **kw)
         return ext.rasterize_gaussians(a["bg"], a["means"], a["col"], a["op"], a["sc"], a["rot"], 1.0, a["cov"], eye, eye, 0.5, 0.5,
-                                       64, 64, a["sh"], 0, z(3), False, False, 0, 4, True, 0, None)
+                                       64, 64, a["sh"], 0, z(3), False, False, 0, 4, True, 0, None, False)
     call()                                                        # the valid call goes through
     with pytest.raises(RuntimeError, match="exactly one of either SHs or precomputed colors"):
         call(col=z(4, 3))
@@ -64,10 +64,10 @@ def test_torch_check_errors_on_device(ext):
         call(rot=z(4, 4, dtype=torch.float64))
     with pytest.raises(RuntimeError, match="viewmatrix must be on"):
         ext.rasterize_gaussians(z(3), z(4, 3), e, z(4), z(4, 3), z(4, 4), 1.0, e, torch.eye(4), eye, 0.5, 0.5, 64, 64, z(4, 1, 3), 0,
-                                z(3), False, False, 0, 4, True, 0, None)
+                                z(3), False, False, 0, 4, True, 0, None, False)
     with pytest.raises(RuntimeError, match="tile rows"):
         ext.rasterize_gaussians(z(3), z(4, 3), e, z(4), z(4, 3), z(4, 4), 1.0, e, eye, eye, 0.5, 0.5, 64, 64, z(4, 1, 3), 0, z(3),
-                                False, False, 3, 9, True, 0, None)
+                                False, False, 3, 9, True, 0, None, False)
 
 
 @pytest.mark.gpu

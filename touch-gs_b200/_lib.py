@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TGS_LIB_PATH") or os.path.join(HERE, "libtgs.so")   # override: A/B builds
 
-TGS_ABI_VERSION = 6
+TGS_ABI_VERSION = 7
 BUF_GEOM, BUF_BINNING, BUF_IMAGE, BUF_TEMP = 0, 1, 2, 3
 LOSS_NONE, LOSS_L1, LOSS_L2 = 0, 1, 2
 LOSS_MODES = {"none": LOSS_NONE, "l1": LOSS_L1, "l2": LOSS_L2}
@@ -27,7 +27,7 @@ class TgsSettings(C.Structure):
         ("sh_degree", C.c_int32), ("sh_coeffs", C.c_int32),
         ("prefiltered", C.c_int32), ("debug", C.c_int32),
         ("tile_row_begin", C.c_int32), ("tile_row_end", C.c_int32),
-        ("depth_normalize", C.c_int32), ("reserved0", C.c_int32), ("rendered_hint", C.c_int64),
+        ("depth_normalize", C.c_int32), ("defer_count", C.c_int32), ("rendered_hint", C.c_int64),
         ("viewmatrix", c_fp), ("projmatrix", c_fp), ("campos", c_fp), ("bg", c_fp),
         ("alpha_max", C.c_float), ("near_z", C.c_float), ("principal_dx", C.c_float), ("principal_dy", C.c_float),
     ]
@@ -105,6 +105,7 @@ SIGNATURES = {
     "tgs_launch_counts": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "tgs_profile_enable": (C.c_int, [C.c_int32]),
     "tgs_profile_read": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "tgs_forward_resolve": (C.c_int, [C.c_int64, C.c_int64, C.POINTER(C.c_int64)]),
     "tgs_mark_visible": (C.c_int, [C.c_int32, c_fp, c_fp, c_fp, c_fp]),
     "tgs_forward": (C.c_int, [C.POINTER(TgsSettings), C.POINTER(TgsGaussians), ALLOC_FN, C.c_void_p,
                               c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, C.POINTER(TgsSaved), c_fp]),

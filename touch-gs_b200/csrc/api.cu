@@ -189,6 +189,53 @@ static uint32_t* pinned_word() {
     return p;
 }
 
+// ---------------------------------------------------------- deferred count (TgsSettings.defer_count)
+// A forward that does not wait for num_rendered parks the D2H copy of the count in a pinned slot with an event and hands
+// out a ticket; the backward (possibly on autograd's thread: the table is global) redeems it.
+namespace {
+struct CountTicket { uint32_t* host = nullptr; cudaEvent_t ev = nullptr; int state = 0; int64_t value = 0; };   // 0 free, 1 pending, 2 resolved
+constexpr int kTickets = 8;
+CountTicket g_tickets[kTickets];
+int g_ticket_next = 0;
+std::mutex g_ticket_mu;
+}  // namespace
+static int ticket_issue(const uint32_t* count_dev, cudaStream_t st, int64_t* ticket) {
+    std::lock_guard<std::mutex> lk(g_ticket_mu);
+    const int k = g_ticket_next;
+    g_ticket_next = (g_ticket_next + 1) % kTickets;
+    CountTicket& t = g_tickets[k];
+    if (!t.host) TGS_CUDA(cudaHostAlloc((void**)&t.host, 64, cudaHostAllocDefault));
+    if (!t.ev) TGS_CUDA(cudaEventCreateWithFlags(&t.ev, cudaEventDisableTiming));
+    if (t.state == 1) TGS_CUDA(cudaEventSynchronize(t.ev));      // an unredeemed ticket 8 forwards old: its copy must land first
+    TGS_CUDA(cudaMemcpyAsync(t.host, count_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    TGS_CUDA(cudaEventRecord(t.ev, st));
+    t.state = 1;
+    *ticket = -(int64_t)(k + 1);
+    return 0;
+}
+extern "C" int tgs_forward_resolve(int64_t ticket, int64_t capacity, int64_t* num_rendered_out) {
+    if (ticket >= 0) { if (num_rendered_out) *num_rendered_out = ticket; return 0; }
+    const int k = (int)(-ticket) - 1;
+    if (k < 0 || k >= kTickets || !num_rendered_out) { tgs_set_error("tgs_forward_resolve: bad ticket"); return TGS_EINVAL; }
+    std::lock_guard<std::mutex> lk(g_ticket_mu);
+    CountTicket& t = g_tickets[k];
+    if (t.state == 0) { tgs_set_error("tgs_forward_resolve: ticket was never issued or has expired"); return TGS_ESTATE; }
+    if (t.state == 1) {
+        TGS_CUDA(cudaEventSynchronize(t.ev));
+        if (t.host[1]) { tgs_set_error("num_rendered does not fit 32 bits (more than 4,294,967,295 tile instances)"); return TGS_EINVAL; }
+        t.value = (int64_t)t.host[0];
+        t.state = 2;
+    }
+    *num_rendered_out = t.value;
+    if (capacity >= 0 && t.value > capacity) {
+        tgs_set_error("deferred speculative forward overflowed: %lld instances rendered, buffers sized for %lld (rendered_hint); "
+                      "its outputs are invalid -- redo the step with a larger hint or without defer_count",
+                      (long long)t.value, (long long)capacity);
+        return TGS_EOVERFLOW;
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------------------ C ABI
 extern "C" int tgs_abi_version(void) { return TGS_ABI_VERSION; }
 extern "C" const char* tgs_last_error(void) { return g_err; }
@@ -249,6 +296,15 @@ extern "C" int tgs_forward(const TgsSettings* s, const TgsGaussians* g, tgs_allo
         rc = tgs_launch_preprocess(cam, s, g, gv, radii, st); if (rc) return rc;
         rc = tgs_depth_order(gv, N, st); if (rc) return rc;
         rc = tgs_bin_count(gv, N, cam.Tx, cam.Ty, cam.row0, cam.row1, temp, iv.ranges, iv.count, st); if (rc) return rc;
+        if (s->rendered_hint > 0 && s->defer_count) {
+            // DEFERRED: the whole forward is enqueued for `hint` slots and the host never waits; the count travels to a
+            // pinned slot behind an event and is checked when the backward redeems the ticket
+            cap = s->rendered_hint;
+            rc = ticket_issue(iv.count, st, &I); if (rc) return rc;
+            rc = tail(cap, cap, true); if (rc) return rc;
+            saved->geom = geom; saved->binning = binning; saved->image = image; saved->num_rendered = I; saved->capacity = cap;
+            return 0;
+        }
         TGS_CUDA(cudaMemcpyAsync(hp, iv.count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         if (s->rendered_hint > 0) {
             // SPECULATIVE: enqueue scatter + pack + render for `hint` slots, THEN wait for the count (event recorded
@@ -284,11 +340,13 @@ extern "C" int tgs_backward_render(const TgsSettings* s, const TgsGaussians* g, 
     if (!dL_dcolor || (g->N > 0 && !screen_grads)) { tgs_set_error("tgs_backward_render: NULL gradient buffers"); return TGS_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
     const TgsCam cam = tgs_make_cam(s);
-    BinView bv = tgs_bin_view(saved->binning, saved->capacity > 0 ? saved->capacity : saved->num_rendered);
+    int64_t I = saved->num_rendered;
+    if (I < 0) { rc = tgs_forward_resolve(I, saved->capacity, &I); if (rc) return rc; }     // deferred forward: redeem the count
+    BinView bv = tgs_bin_view(saved->binning, saved->capacity > 0 ? saved->capacity : I);
     ImageView iv = tgs_image_view(saved->image, cam.W, cam.H);
     if (g->N > 0) TGS_CUDA(cudaMemsetAsync(screen_grads, 0, sizeof(float) * TGS_NGRAD * (size_t)g->N, st));
     GeomView gvb = tgs_geom_view(saved->geom, g->N);
-    return tgs_launch_render_bwd(cam, s, gvb.records, bv, iv, saved->num_rendered, dL_dcolor, dL_ddepth, dL_dalpha, touch, residual_out,
+    return tgs_launch_render_bwd(cam, s, gvb.records, bv, iv, I, dL_dcolor, dL_ddepth, dL_dalpha, touch, residual_out,
                                  screen_grads, st);
 }
 

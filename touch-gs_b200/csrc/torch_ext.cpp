@@ -78,7 +78,7 @@ Inputs make_inputs(const Tensor& bg, const Tensor& means3D, const Tensor& colors
                    const Tensor& rotations, double scale_modifier, const Tensor& cov3D_precomp, const Tensor& viewmatrix,
                    const Tensor& projmatrix, double tanfovx, double tanfovy, int64_t H, int64_t W, const Tensor& sh,
                    int64_t degree, const Tensor& campos, bool prefiltered, bool debug, int64_t row0, int64_t row1,
-                   bool depth_normalize, int64_t rendered_hint) {
+                   bool depth_normalize, int64_t rendered_hint, bool defer_count = false) {
     TORCH_CHECK(means3D.defined() && means3D.dim() == 2 && means3D.size(1) == 3, "means3D must have dimensions (num_points, 3)");
     TORCH_CHECK(means3D.is_cuda(), "touchgs_b200 rasterizer is CUDA-only (no CPU fallback); means3D is on ", means3D.device());
     const c10::Device dev = means3D.device();
@@ -116,6 +116,7 @@ Inputs make_inputs(const Tensor& bg, const Tensor& means3D, const Tensor& colors
     s.prefiltered = prefiltered; s.debug = debug;
     s.tile_row_begin = (int32_t)row0; s.tile_row_end = (int32_t)row1;
     s.depth_normalize = depth_normalize; s.rendered_hint = rendered_hint > 0 ? rendered_hint : 0;
+    s.defer_count = (defer_count && rendered_hint > 0) ? 1 : 0;
     s.viewmatrix = fp(in.view); s.projmatrix = fp(in.proj); s.campos = fp(in.campos); s.bg = fp(in.bg);
     TgsGaussians& g = in.g;
     g.N = (int32_t)N;
@@ -133,10 +134,10 @@ rasterize_gaussians(const Tensor& bg, const Tensor& means3D, const Tensor& color
                     const Tensor& projmatrix, double tanfovx, double tanfovy, int64_t H, int64_t W, const Tensor& sh,
                     int64_t degree, const Tensor& campos, bool prefiltered, bool debug,
                     int64_t tile_row_begin, int64_t tile_row_end, bool depth_normalize, int64_t rendered_hint,
-                    const OptT& touch_depth) {
+                    const OptT& touch_depth, bool defer_count) {
     Inputs in = make_inputs(bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
                             projmatrix, tanfovx, tanfovy, H, W, sh, degree, campos, prefiltered, debug, tile_row_begin,
-                            tile_row_end, depth_normalize, rendered_hint);
+                            tile_row_end, depth_normalize, rendered_hint, defer_count);
     const c10::Device dev = in.means3D.device();
     c10::cuda::CUDAGuard guard(dev);
     const int64_t N = in.means3D.size(0), Ty = (H + 15) / 16;
@@ -367,6 +368,41 @@ Tensor touch_loss_value(const Tensor& residual, const OptT& weight, int64_t H, i
     return out;
 }
 
+// (1-l) * mean|C - C*| + l * (1 - mean SSIM) on the loss rows; returns (loss scalar, derivative maps for the backward)
+std::tuple<Tensor, Tensor> photometric_loss_forward(const Tensor& color, const Tensor& gt, int64_t row_begin, int64_t row_end,
+                                                    double lambda_dssim) {
+    TORCH_CHECK(color.defined() && color.is_cuda(), "color: touchgs_b200 train ops are CUDA-only (no CPU fallback)");
+    const c10::Device dev = color.device();
+    c10::cuda::CUDAGuard guard(dev);
+    TORCH_CHECK(color.dim() == 3 && color.size(0) == 3 && gt.sizes() == color.sizes(), "color / gt must both be [3,H,W], got ",
+                color.sizes(), " / ", gt.sizes());
+    const int64_t H = color.size(1), W = color.size(2);
+    Tensor c = f32(color, "color", {3, H, W}, dev), g = f32(gt, "gt", {3, H, W}, dev);
+    auto fo = at::TensorOptions().dtype(at::kFloat).device(dev);
+    Tensor dmaps = at::empty({(int64_t)tgs_photometric_scratch_floats((int32_t)W, (int32_t)H)}, fo);
+    Tensor sums = at::empty({2}, fo.dtype(at::kDouble));
+    Tensor loss = at::empty({}, fo);
+    check_rc(tgs_photometric_loss_forward(fp(c), fp(g), (int32_t)W, (int32_t)H, (int32_t)row_begin, (int32_t)row_end,
+                                          (float)lambda_dssim, dmaps.data_ptr<float>(), sums.data_ptr<double>(),
+                                          loss.data_ptr<float>(), cur_stream(dev)), "tgs_photometric_loss_forward");
+    return std::make_tuple(loss, dmaps);
+}
+
+Tensor photometric_loss_backward(const Tensor& color, const Tensor& gt, const Tensor& dmaps, int64_t row_begin, int64_t row_end,
+                                 int64_t out_row_begin, int64_t out_row_end, double lambda_dssim, const Tensor& grad_out) {
+    const c10::Device dev = color.device();
+    c10::cuda::CUDAGuard guard(dev);
+    const int64_t H = color.size(1), W = color.size(2);
+    Tensor c = f32(color, "color", {3, H, W}, dev), g = f32(gt, "gt", {3, H, W}, dev);
+    Tensor go = f32(grad_out.reshape({-1}), "grad_out", {-1}, dev);
+    const bool full = (out_row_begin == 0 && out_row_end == H);
+    Tensor dcolor = full ? at::empty_like(c) : at::zeros_like(c);
+    check_rc(tgs_photometric_loss_backward(fp(c), fp(g), fp(dmaps), (int32_t)W, (int32_t)H, (int32_t)row_begin, (int32_t)row_end,
+                                           (int32_t)out_row_begin, (int32_t)out_row_end, (float)lambda_dssim, fp(go),
+                                           dcolor.data_ptr<float>(), cur_stream(dev)), "tgs_photometric_loss_backward");
+    return dcolor;
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -376,7 +412,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("backward_render", &backward_render);
     m.def("backward_preprocess", &backward_preprocess);
     m.def("mark_visible", &mark_visible);
+    m.def("resolve_count", [](int64_t ticket, int64_t capacity) {
+        int64_t n = 0;
+        check_rc(tgs_forward_resolve(ticket, capacity, &n), "tgs_forward_resolve");
+        return n;
+    });
     m.def("touch_loss_scale", &touch_loss_scale);
     m.def("touch_loss_value", &touch_loss_value);
+    m.def("photometric_loss_forward", &photometric_loss_forward);
+    m.def("photometric_loss_backward", &photometric_loss_backward);
     m.def("abi_version", []() { return tgs_abi_version(); });
 }

@@ -62,7 +62,7 @@ def _settings(H, W, keep, *, dev, fx=None, fy=None, cx=None, cy=None, view=None,
         tanfovx=1.0 if fx is None else float(W) / (2.0 * float(fx)),
         tanfovy=1.0 if fy is None else float(H) / (2.0 * float(fy)),
         scale_modifier=float(glob_scale), sh_degree=0, sh_coeffs=0, prefiltered=0, debug=0,
-        tile_row_begin=0, tile_row_end=0, depth_normalize=0, reserved0=0, rendered_hint=0,
+        tile_row_begin=0, tile_row_end=0, depth_normalize=0, defer_count=0, rendered_hint=0,
         viewmatrix=None if view is None else view.data_ptr(), projmatrix=None if proj is None else proj.data_ptr(),
         campos=zero3.data_ptr(), bg=bg.data_ptr(), alpha_max=ALPHA_MAX, near_z=float(clip_thresh),
         principal_dx=0.0 if cx is None else float(cx) - 0.5 * float(W),

@@ -63,6 +63,9 @@ class TouchOptions(NamedTuple):
     return_touch_loss: bool = False                # True: the operator also returns the touch loss as a DIFFERENTIABLE
                                                    # scalar; the fused gradient is then scaled by that scalar's upstream
                                                    # gradient (0 if the caller leaves it out of the objective)
+    defer_count: bool = False                      # with rendered_hint > 0: the forward never waits for num_rendered (the host
+                                                   # stays a full step ahead of the GPU); the count is checked when the backward
+                                                   # runs and an overflowed hint raises there (redo the step with a larger hint)
     loss_grad_scale: object = None                 # injected mode (return_touch_loss=False): explicit upstream scale of
                                                    # the objective (float or 0-dim tensor), e.g. a GradScaler's scale or
                                                    # 1/accumulation_steps; None = 1
@@ -159,7 +162,8 @@ def _make_settings(rs: GaussianRasterizationSettings, opt: TouchOptions, K: int,
         tanfovx=float(rs.tanfovx), tanfovy=float(rs.tanfovy), scale_modifier=float(rs.scale_modifier),
         sh_degree=int(rs.sh_degree), sh_coeffs=int(K), prefiltered=int(bool(rs.prefiltered)),
         debug=int(bool(rs.debug)), tile_row_begin=r0, tile_row_end=r1,
-        depth_normalize=int(bool(opt.depth_normalize)), reserved0=0,
+        depth_normalize=int(bool(opt.depth_normalize)),
+        defer_count=int(bool(opt.defer_count) and int(opt.rendered_hint or 0) > 0),
         rendered_hint=max(0, int(opt.rendered_hint or 0)),
         viewmatrix=vm.data_ptr(), projmatrix=pmx.data_ptr(), campos=cam.data_ptr(), bg=bg.data_ptr())
     return s, (r0, r1, Ty)
@@ -228,7 +232,7 @@ def _forward_ext(ext, ctx, means3D, sh, colors_precomp, opacities, scales, rotat
     cov_ = e if cov3Ds_precomp is None else cov3Ds_precomp
     args = (rs.bg, means3D, col_, opacities, sc_, rot_, float(rs.scale_modifier), cov_, rs.viewmatrix, rs.projmatrix,
             float(rs.tanfovx), float(rs.tanfovy), H, W, sh_, int(rs.sh_degree), rs.campos, bool(rs.prefiltered), bool(rs.debug),
-            r0, r1, bool(opt.depth_normalize), max(0, int(opt.rendered_hint or 0)), touch_depth)
+            r0, r1, bool(opt.depth_normalize), max(0, int(opt.rendered_hint or 0)), touch_depth, bool(opt.defer_count))
     try:
         num_rendered, color, depth, alpha, radii, geom, binning, image, resid, capacity = ext.rasterize_gaussians(*args)
     except Exception:
@@ -565,7 +569,7 @@ class GaussianRasterizer(torch.nn.Module):
     def __init__(self, raster_settings: GaussianRasterizationSettings):
         super().__init__()
         self.raster_settings = raster_settings
-        self.last_num_rendered = 0
+        self._last = (0, 0)
 
     def markVisible(self, positions: torch.Tensor) -> torch.Tensor:
         """bool[N]: view-space z > 0.2 for the module's camera."""
@@ -591,7 +595,7 @@ class GaussianRasterizer(torch.nn.Module):
                 depth_loss: str = "none", depth_loss_mult: float = 1.0, depth_normalize: bool = True,
                 depth_loss_norm: Optional[float] = None, tile_rows=None, process_group=None,
                 rendered_hint: int = 0, touch_rows=None, peer_exchange=None, return_touch_loss: bool = False,
-                loss_grad_scale=None):
+                loss_grad_scale=None, defer_count: bool = False):
         if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
             raise Exception("Please provide excatly one of either SHs or precomputed colors!")
         if ((scales is None or rotations is None) and cov3D_precomp is None) or \
@@ -601,11 +605,27 @@ class GaussianRasterizer(torch.nn.Module):
         info = {}
         opt = TouchOptions(touch_depth, touch_weight, depth_loss, depth_loss_mult, depth_normalize,
                            depth_loss_norm, tile_rows, process_group, rendered_hint, info, touch_rows, peer_exchange,
-                           bool(return_touch_loss), loss_grad_scale)
+                           bool(return_touch_loss), bool(defer_count), loss_grad_scale)
         out = rasterize_gaussians(means3D, means2D,
                                   e if shs is None else shs, e if colors_precomp is None else colors_precomp,
                                   opacities, e if scales is None else scales, e if rotations is None else rotations,
                                   e if cov3D_precomp is None else cov3D_precomp, self.raster_settings, opt)
-        # instance count of this call: feed it back as `rendered_hint` the next time this view is rendered
-        self.last_num_rendered = info.get("num_rendered", 0)
+        # instance count of this call: feed it back as `rendered_hint` the next time this view is rendered.  After a deferred
+        # forward it is a (negative) ticket that `last_num_rendered` redeems on first access -- read it AFTER backward
+        self._last = (info.get("num_rendered", 0), info.get("capacity", 0))
         return out
+
+    @property
+    def last_num_rendered(self) -> int:
+        n, cap = self._last
+        if n < 0:
+            import ctypes as _C
+            v = _C.c_int64(0)
+            L.check(L.load().tgs_forward_resolve(int(n), int(cap), _C.byref(v)), "tgs_forward_resolve")
+            n = int(v.value)
+            self._last = (n, cap)
+        return n
+
+    @last_num_rendered.setter
+    def last_num_rendered(self, v):
+        self._last = (int(v), 0)

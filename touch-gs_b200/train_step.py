@@ -40,6 +40,15 @@ def _cuda_only(t: torch.Tensor, name: str):
 class _PhotometricLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, color, gt, lambda_dssim, rows, out_rows):
+        ext = L.load_ext()
+        if ext is not None:                      # default binding: one C++ call (checks, allocations, launch)
+            H = int(color.shape[1]) if color.dim() == 3 else 0
+            r0, r1 = (0, H) if rows is None else (int(rows[0]), int(rows[1]))
+            loss, dmaps = ext.photometric_loss_forward(color, gt, r0, r1, float(lambda_dssim))
+            ctx.save_for_backward(color, gt, dmaps)
+            ctx.args = (int(color.shape[2]), H, r0, r1, float(lambda_dssim), out_rows)
+            ctx.ext = ext
+            return loss
         lib = L.load()
         color, gt = _cuda_only(color, "color"), _cuda_only(gt, "gt")
         if color.dim() != 3 or color.shape[0] != 3 or gt.shape != color.shape:
@@ -60,10 +69,12 @@ class _PhotometricLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        lib = L.load()
         color, gt, dmaps = ctx.saved_tensors
         W, H, r0, r1, lam, out_rows = ctx.args
         o0, o1 = (0, H) if out_rows is None else (int(out_rows[0]), int(out_rows[1]))
+        if getattr(ctx, "ext", None) is not None:
+            return ctx.ext.photometric_loss_backward(color, gt, dmaps, r0, r1, o0, o1, lam, g), None, None, None, None
+        lib = L.load()
         dev = color.device
         with torch.cuda.device(dev):
             g = g.reshape(1).to(torch.float32).contiguous()
