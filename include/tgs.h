@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TGS_ABI_VERSION 7
+#define TGS_ABI_VERSION 8
 
 #define TGS_EINVAL   (-1)   /* bad argument combination / shape */
 #define TGS_ENOMEM   (-2)   /* allocator callback returned NULL */
@@ -71,6 +71,17 @@ typedef struct TgsSettings {
                                * a larger hint (a trainer's hint = the view's previous count + a margin never overflows in steady
                                * state).  Keeps the host a full step ahead of the GPU: what a tile-row shard with little work per
                                * rank needs. */
+    int32_t contrib_flags;    /* 1: every screen-gradient buffer handed to tgs_backward_render / tgs_backward_preprocess /
+                               * tgs_backward_preprocess_gather is tgs_screen_grad_bytes(N, 1) bytes long: the [N,10] rows
+                               * followed (at TGS_SCREEN_GRAD_FLAG_OFFSET(N)) by one CONTRIBUTOR byte per Gaussian, set by
+                               * BACKWARD::render for every Gaussian some pixel blended.  The chain rule then reads neither
+                               * the row nor the parameters of a non-contributor (its gradients are exactly zero), and the
+                               * multi-GPU gather asks a peer only for the rows that peer flagged: in a dense scene most
+                               * Gaussians lie behind the depth at which their tiles saturate (c3: 86 %).
+                               * 0: plain [N,10] buffers (required when the buffers are summed by an all-reduce; also the
+                               * better choice on ONE GPU, where the chain rule spots the all-zero rows itself and the
+                               * bytes would only cost BACKWARD::render 3 %).
+                               * (occupies what was alignment padding: the struct layout is unchanged) */
     int64_t rendered_hint;    /* 0: synchronous sizing (read num_rendered, then bin).  > 0: SPECULATIVE mode: the
                                * binning buffers are sized for this many instances and the binning + render kernels
                                * are enqueued BEFORE the host waits for the real count (the wait is on an event
@@ -190,8 +201,11 @@ int tgs_forward(const TgsSettings* s, const TgsGaussians* g,
  * dL_dcolor [3,H,W]; dL_ddepth / dL_dalpha [H,W] or NULL (external autograd grads on the
  * returned depth / alpha);  residual_out [H,W] or NULL.
  * screen_grads [N,10] = (dx,dy (pixel units), dA,dB,dC, dopacity, dr,dg,db, ddepth) is
- * ZEROED then accumulated: this is the buffer the multi-GPU path all-reduces.
+ * ZEROED then accumulated: this is the buffer the multi-GPU path exchanges.
+ * With s->contrib_flags the buffer is tgs_screen_grad_bytes(N, 1) bytes: rows, then the contributor bytes.
  */
+#define TGS_SCREEN_GRAD_FLAG_OFFSET(N) ((((size_t)(N) * 40u) + 127u) / 128u * 128u)   /* bytes; flags are 128-byte aligned */
+size_t tgs_screen_grad_bytes(int32_t N, int32_t contrib_flags);
 int tgs_backward_render(const TgsSettings* s, const TgsGaussians* g, const TgsSaved* saved,
                         const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
                         const TgsTouch* touch, float* residual_out,
@@ -208,6 +222,8 @@ int tgs_backward_preprocess(const TgsSettings* s, const TgsGaussians* g, const T
  * peer_screen_grads_host[r] (device pointers valid on THIS device: peer-mapped / symmetric memory over NVLink,
  * the local rank's own buffer included).  For every Gaussian the kernel reads the rows of exactly those ranks whose
  * band its tile-row span touches and sums them in ascending rank order -- no all-reduce, no second kernel.
+ * With s->contrib_flags (every peer buffer carries its contributor bytes) a warp first fetches the 32 flag bytes of its
+ * Gaussians from each peer (one sector per peer) and then asks only for the rows that peer actually wrote.
  * The caller must have synchronised the ranks (all tgs_backward_render calls finished) before this runs.
  */
 #define TGS_MAX_PEERS 8

@@ -38,6 +38,22 @@ def test_layouts_are_aligned_and_monotone(tgs_lib):
     assert i.total >= 6 * 4 * 5000 and i.count >= i.ranges + 7 * 4 * 8          # 7 x 4 tiles of (start, end)
 
 
+def test_screen_grad_buffer_size_and_settings_layout(tgs_lib):
+    """contrib_flags sits in what used to be alignment padding of TgsSettings; the Python size helper mirrors the C one."""
+    L = T._lib
+    assert L.TgsSettings.defer_count.offset == 48 and L.TgsSettings.contrib_flags.offset == 52
+    assert L.TgsSettings.rendered_hint.offset == 56
+    for n in (0, 1, 3, 127, 128, 129, 30000, 1_000_000, 5_000_001):
+        for f in (0, 1):
+            b = tgs_lib.tgs_screen_grad_bytes(n, f)
+            assert b == 4 * L.screen_grad_floats(n, bool(f)), (n, f)
+            if n and f:
+                off = (n * 40 + 127) // 128 * 128
+                assert b >= off + n and off % 128 == 0 and b % 128 == 0
+            elif n:
+                assert b == 40 * n
+
+
 def test_argument_errors_without_gpu(tgs_lib):
     L = T._lib
     s = L.TgsSettings(image_width=64, image_height=64, tanfovx=0.5, tanfovy=0.5, scale_modifier=1.0)

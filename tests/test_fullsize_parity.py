@@ -177,10 +177,13 @@ class _Abi:
         return g, self.L.TgsGrads(**{k: v.data_ptr() for k, v in g.items()})
 
 
+@pytest.mark.parametrize("flags", [True, False], ids=["contrib_flags", "plain_rows"])
 @pytest.mark.parametrize("world", [2, 8])
-def test_emulated_peer_gather_is_bit_identical_to_summed_buffers(world):
+def test_emulated_peer_gather_is_bit_identical_to_summed_buffers(world, flags):
     """One device plays all ranks: rank r renders tile rows bands[r] into ITS [N,10] buffer; the gather kernel reads
-    only the buffers of the ranks whose band a Gaussian's tile-row span touches, in ascending rank order."""
+    only the buffers of the ranks whose band a Gaussian's tile-row span touches, in ascending rank order.
+    `flags`: the buffers carry the contributor bytes behind the rows (TgsSettings.contrib_flags, what PeerScreenGrads
+    allocates): the gather fetches the 32 bytes of a warp from every peer and asks only for the rows a peer wrote."""
     H, W, deg, N = 272, 320, 3, 30000
     sc = synth.make_scene(N, deg, 0.005, 0.06, seed=3)
     cam = synth.look_at_camera(W, H, (0.4, 0.3, -3.0))
@@ -188,14 +191,26 @@ def test_emulated_peer_gather_is_bit_identical_to_summed_buffers(world):
     g = torch.Generator().manual_seed(1)
     grgb = (torch.rand(3, H, W, generator=g) / (3 * H * W)).to(DEV)
     bands = T.sharding.even_bands(H, world)
-    bufs, fws = [], []
+    raw, bufs, fws = [], [], []
+    nf = abi.L.screen_grad_floats(N, flags)
+    assert nf * 4 == abi.lib.tgs_screen_grad_bytes(N, 1 if flags else 0)
     for b in bands:
         fw = abi.forward(b)
-        sg = torch.full((N, 10), 7.0, device=DEV)                # zeroed by the library
+        fw["settings"].contrib_flags = 1 if flags else 0
+        sg = torch.full((nf,), 7.0, device=DEV)                  # zeroed by the library
         abi.backward_render(fw, grgb, sg)
-        bufs.append(sg)
+        raw.append(sg)
+        bufs.append(sg[: 10 * N].view(N, 10))
         fws.append(fw)
     torch.cuda.synchronize()
+    if flags:
+        off = (N * 40 + 127) // 128 * 128
+        for sg, rows_ in zip(raw, bufs):
+            fl = sg.view(torch.uint8)[off: off + N]
+            assert bool((fl <= 1).all())
+            assert bool(((rows_ != 0).any(1) <= (fl == 1)).all()), "a non-zero row without its contributor byte"
+            assert int(fl.sum()) < N, "every Gaussian flagged: the test would not exercise the skip"
+            assert bool((sg.view(torch.uint8)[off + N:] == 0).all())     # the padding behind the flags is zeroed too
     assert sum(int((b.abs().sum(1) > 0).sum()) for b in bufs) > N // 4
     # Gaussians straddling a band border have partial sums on two ranks
     both = ((bufs[0].abs().sum(1) > 0) & (bufs[1].abs().sum(1) > 0)).sum()
@@ -207,10 +222,12 @@ def test_emulated_peer_gather_is_bit_identical_to_summed_buffers(world):
     p = lambda t: C.c_void_p(t.data_ptr())
     fw0 = fws[world // 2]                                         # any rank's saved geometry serves: it is band independent
     g_sum, gr_sum = abi.grads()
+    fw0["settings"].contrib_flags = 0                             # the summed buffer is plain [N,10]
     L.check(lib.tgs_backward_preprocess(C.byref(fw0["settings"]), C.byref(fw0["gauss"]), C.byref(fw0["saved"]), p(fw0["radii"]),
                                         p(total), C.byref(gr_sum), abi.stream), "tgs_backward_preprocess")
+    fw0["settings"].contrib_flags = 1 if flags else 0
     g_gat, gr_gat = abi.grads()
-    ptrs = (C.c_void_p * world)(*[b.data_ptr() for b in bufs])
+    ptrs = (C.c_void_p * world)(*[b.data_ptr() for b in raw])
     rows = (C.c_int32 * (2 * world))(*[int(v) for b in bands for v in b])
     L.check(lib.tgs_backward_preprocess_gather(C.byref(fw0["settings"]), C.byref(fw0["gauss"]), C.byref(fw0["saved"]),
                                                p(fw0["radii"]), ptrs, rows, world, C.byref(gr_gat), abi.stream),
@@ -221,7 +238,8 @@ def test_emulated_peer_gather_is_bit_identical_to_summed_buffers(world):
     assert float(g_gat["dmeans3D"].abs().max()) > 0
     # and both equal the unsharded backward within the float bar (different summation order of the atomics)
     fwf = abi.forward(None)
-    sgf = torch.empty(N, 10, device=DEV)
+    fwf["settings"].contrib_flags = 1 if flags else 0            # single buffer with / without the contributor bytes
+    sgf = torch.empty(nf, device=DEV)
     abi.backward_render(fwf, grgb, sgf)
     g_full, gr_full = abi.grads()
     L.check(lib.tgs_backward_preprocess(C.byref(fwf["settings"]), C.byref(fwf["gauss"]), C.byref(fwf["saved"]), p(fwf["radii"]),

@@ -11,11 +11,22 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TGS_LIB_PATH") or os.path.join(HERE, "libtgs.so")   # override: A/B builds
 
-TGS_ABI_VERSION = 7
+TGS_ABI_VERSION = 8
 BUF_GEOM, BUF_BINNING, BUF_IMAGE, BUF_TEMP = 0, 1, 2, 3
 LOSS_NONE, LOSS_L1, LOSS_L2 = 0, 1, 2
 LOSS_MODES = {"none": LOSS_NONE, "l1": LOSS_L1, "l2": LOSS_L2}
 NGRAD = 10
+
+
+def screen_grad_floats(N: int, contrib_flags: bool = True) -> int:
+    """float32 elements of a screen-gradient buffer (include/tgs.h: tgs_screen_grad_bytes): the [N,10] rows, plus --
+    with TgsSettings.contrib_flags -- one contributor byte per Gaussian at the 128-byte aligned offset behind them"""
+    N = int(N)
+    if N <= 0:
+        return 0
+    if not contrib_flags:
+        return NGRAD * N
+    return ((N * 4 * NGRAD + 127) // 128 * 128 + (N + 127) // 128 * 128) // 4
 
 c_fp = C.c_void_p  # all device pointers travel as void*
 
@@ -27,7 +38,8 @@ class TgsSettings(C.Structure):
         ("sh_degree", C.c_int32), ("sh_coeffs", C.c_int32),
         ("prefiltered", C.c_int32), ("debug", C.c_int32),
         ("tile_row_begin", C.c_int32), ("tile_row_end", C.c_int32),
-        ("depth_normalize", C.c_int32), ("defer_count", C.c_int32), ("rendered_hint", C.c_int64),
+        ("depth_normalize", C.c_int32), ("defer_count", C.c_int32), ("contrib_flags", C.c_int32),
+        ("rendered_hint", C.c_int64),
         ("viewmatrix", c_fp), ("projmatrix", c_fp), ("campos", c_fp), ("bg", c_fp),
         ("alpha_max", C.c_float), ("near_z", C.c_float), ("principal_dx", C.c_float), ("principal_dy", C.c_float),
     ]
@@ -109,6 +121,7 @@ SIGNATURES = {
     "tgs_mark_visible": (C.c_int, [C.c_int32, c_fp, c_fp, c_fp, c_fp]),
     "tgs_forward": (C.c_int, [C.POINTER(TgsSettings), C.POINTER(TgsGaussians), ALLOC_FN, C.c_void_p,
                               c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, C.POINTER(TgsSaved), c_fp]),
+    "tgs_screen_grad_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "tgs_backward_render": (C.c_int, [C.POINTER(TgsSettings), C.POINTER(TgsGaussians), C.POINTER(TgsSaved),
                                       c_fp, c_fp, c_fp, C.POINTER(TgsTouch), c_fp, c_fp, c_fp]),
     "tgs_backward_preprocess": (C.c_int, [C.POINTER(TgsSettings), C.POINTER(TgsGaussians), C.POINTER(TgsSaved),

@@ -331,6 +331,12 @@ extern "C" int tgs_forward(const TgsSettings* s, const TgsGaussians* g, tgs_allo
     return 0;
 }
 
+extern "C" size_t tgs_screen_grad_bytes(int32_t N, int32_t contrib_flags) {
+    if (N <= 0) return 0;
+    if (!contrib_flags) return sizeof(float) * TGS_NGRAD * (size_t)N;
+    return TGS_SCREEN_GRAD_FLAG_OFFSET(N) + ((size_t)N + 127u) / 128u * 128u;
+}
+
 extern "C" int tgs_backward_render(const TgsSettings* s, const TgsGaussians* g, const TgsSaved* saved,
                                    const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
                                    const TgsTouch* touch, float* residual_out, float* screen_grads, void* stream) {
@@ -344,10 +350,11 @@ extern "C" int tgs_backward_render(const TgsSettings* s, const TgsGaussians* g, 
     if (I < 0) { rc = tgs_forward_resolve(I, saved->capacity, &I); if (rc) return rc; }     // deferred forward: redeem the count
     BinView bv = tgs_bin_view(saved->binning, saved->capacity > 0 ? saved->capacity : I);
     ImageView iv = tgs_image_view(saved->image, cam.W, cam.H);
-    if (g->N > 0) TGS_CUDA(cudaMemsetAsync(screen_grads, 0, sizeof(float) * TGS_NGRAD * (size_t)g->N, st));
+    if (g->N > 0) TGS_CUDA(cudaMemsetAsync(screen_grads, 0, tgs_screen_grad_bytes(g->N, s->contrib_flags), st));
     GeomView gvb = tgs_geom_view(saved->geom, g->N);
+    uint8_t* flags = (s->contrib_flags && g->N > 0) ? (uint8_t*)screen_grads + TGS_SCREEN_GRAD_FLAG_OFFSET(g->N) : nullptr;
     return tgs_launch_render_bwd(cam, s, gvb.records, bv, iv, I, dL_dcolor, dL_ddepth, dL_dalpha, touch, residual_out,
-                                 screen_grads, st);
+                                 screen_grads, flags, st);
 }
 
 extern "C" int tgs_backward_preprocess(const TgsSettings* s, const TgsGaussians* g, const TgsSaved* saved,
@@ -364,7 +371,8 @@ extern "C" int tgs_backward_preprocess(const TgsSettings* s, const TgsGaussians*
     if (g->cov3D_precomp && !grads->dcov3D) { tgs_set_error("dcov3D required when cov3D_precomp given"); return TGS_EINVAL; }
     const TgsCam cam = tgs_make_cam(s);
     GeomView gv = tgs_geom_view(saved->geom, g->N);
-    return tgs_launch_preprocess_bwd(cam, s, g, gv, radii, screen_grads, nullptr, nullptr, 0, grads, (cudaStream_t)stream);
+    return tgs_launch_preprocess_bwd(cam, s, g, gv, radii, screen_grads, nullptr, nullptr, 0, s->contrib_flags != 0, grads,
+                                     (cudaStream_t)stream);
 }
 
 extern "C" int tgs_backward_preprocess_gather(const TgsSettings* s, const TgsGaussians* g, const TgsSaved* saved,
@@ -388,7 +396,7 @@ extern "C" int tgs_backward_preprocess_gather(const TgsSettings* s, const TgsGau
     const TgsCam cam = tgs_make_cam(s);
     GeomView gv = tgs_geom_view(saved->geom, g->N);
     return tgs_launch_preprocess_bwd(cam, s, g, gv, radii, nullptr, peer_screen_grads_host, peer_tile_rows_host, world,
-                                     grads, (cudaStream_t)stream);
+                                     s->contrib_flags != 0, grads, (cudaStream_t)stream);
 }
 
 extern "C" int tgs_backward(const TgsSettings* s, const TgsGaussians* g, const TgsSaved* saved, const int32_t* radii,

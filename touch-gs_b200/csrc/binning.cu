@@ -20,6 +20,10 @@
 //      and write the Gaussian id to its final position.  Order inside a tile = order of the walk = depth order.
 // Every tile's list is then one contiguous run of ids; the compositing kernels (render.cu) TMA-copy the ids and gather
 // the 48-byte per-Gaussian records by id, so no per-instance copy of the records is ever written.
+// Gaussians that emit nothing sort to the end of the depth order (key 0xFFFFFFFF), so only the leading chunks hold
+// emitters: k_bin_count finds the number of LIVE chunks on the device (no host round trip), and the prefix and the
+// scatter visit only those -- on a rank of the tile-row shard the whole chain costs what its band's emitters cost,
+// not what the N replicated Gaussians cost.
 // Tiles are processed in bands of tile rows (count: <= 8192 tiles = 32 KB of counters per CTA; scatter: ~1024 tiles
 // per single-warp unit) so any image size fits.
 //
@@ -110,11 +114,22 @@ __device__ __forceinline__ uint32_t magic_of(uint32_t w) { return w > 1 ? (uint3
 // x by warp scans, along y by one thread per column, fused with the write of the chunk's row of the count matrix)
 // turns them into coverage counts: 4 atomics per Gaussian instead of ~11 (c3) / ~33 (c5).
 __global__ void __launch_bounds__(256)
-k_bin_count(int N, int chunk, const uint32_t* __restrict__ order, const uint32_t* __restrict__ tiles,
-            const uint2* __restrict__ rect, int Tx, int row_begin, int row_end, int rows_per_band, int T,
-            uint32_t* __restrict__ cnt, uint2* __restrict__ span_sorted) {
+k_bin_count(int N, int chunk, const uint32_t* __restrict__ order, const uint32_t* __restrict__ keys_sorted,
+            const uint32_t* __restrict__ tiles, const uint2* __restrict__ rect, int Tx, int row_begin, int row_end,
+            int rows_per_band, int T, uint32_t* __restrict__ cnt, uint2* __restrict__ span_sorted,
+            uint32_t* __restrict__ live_chunks) {
     extern __shared__ int diff[];                      // [(rows+1)][Tx+1]
     const int band = blockIdx.y;
+    {   // the keys are sorted: a chunk whose first key is "emits nothing" is dead, and so is every chunk behind it
+        const int head = blockIdx.x * chunk;
+        const bool live = keys_sorted[head] != kFull;
+        if (band == 0 && threadIdx.x == 0) {
+            // exactly one chunk is the last live one (or chunk 0 is dead: nothing is rendered at all)
+            if (live && (head + chunk >= N || keys_sorted[head + chunk] == kFull)) *live_chunks = blockIdx.x + 1;
+            if (!live && blockIdx.x == 0) *live_chunks = 0;
+        }
+        if (!live) return;                             // its row of the count matrix is never read
+    }
     const int r0 = row_begin + band * rows_per_band, r1 = min(row_end, r0 + rows_per_band);
     const int rows = r1 - r0, S = Tx + 1;
     for (int t = threadIdx.x; t < (rows + 1) * S; t += 256) diff[t] = 0;
@@ -171,8 +186,10 @@ k_bin_count(int N, int chunk, const uint32_t* __restrict__ order, const uint32_t
 // ---- 2a. per tile column: exclusive prefix over the chunks (in place) and the column total.
 // CTA = 32 tile columns x 8 chunk slices (a warp reads one 128-byte row segment per chunk).
 __global__ void __launch_bounds__(256)
-k_bin_prefix(int nchunks, int T, int t_begin, int t_end, uint32_t* __restrict__ cnt, uint32_t* __restrict__ totals) {
+k_bin_prefix(const uint32_t* __restrict__ live_chunks, int T, int t_begin, int t_end, uint32_t* __restrict__ cnt,
+             uint32_t* __restrict__ totals) {
     __shared__ uint32_t part[8][32];
+    const int nchunks = (int)*live_chunks;             // written by k_bin_count
     const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const int t = t_begin + blockIdx.x * 32 + lane;
     const int per = (nchunks + 7) / 8;
@@ -266,12 +283,14 @@ template <int kSub>
 __global__ void __launch_bounds__(32 * kSub)
 k_bin_scatter(int N, int chunk, int nbands, const uint32_t* __restrict__ order, const uint2* __restrict__ span_sorted,
               int Tx, int row_begin, int row_end, int rows_per_band, int T, const uint32_t* __restrict__ cnt,
-              const uint2* __restrict__ ranges, uint32_t cap, uint32_t* __restrict__ vals) {
+              const uint2* __restrict__ ranges, const uint32_t* __restrict__ live_chunks, uint32_t cap,
+              uint32_t* __restrict__ vals) {
     extern __shared__ __align__(16) uint32_t smem_u32[];
     __shared__ Staged stage_all[kSub][32];
     __shared__ uint32_t stage_id_all[kSub][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int chunk_id = blockIdx.x / nbands, band = blockIdx.x - chunk_id * nbands;
+    if (chunk_id >= (int)*live_chunks) return;          // nothing behind the last emitter of the depth order
     Staged* stage = stage_all[warp];
     uint32_t* stage_id = stage_id_all[warp];
     const int band_tiles = rows_per_band * Tx;
@@ -415,7 +434,11 @@ size_t tgs_depth_sort_temp_bytes(int N) {
 size_t tgs_bin_temp_bytes(int N, int Tx, int Ty) {
     const Plan p = make_plan(N, Tx, Ty);               // nchunks does not depend on the rendered rows
     const size_t T = (size_t)Tx * Ty;
-    return tgs_align_up((size_t)p.nchunks * T * sizeof(uint32_t)) + tgs_align_up(T * sizeof(uint32_t));
+    return tgs_align_up((size_t)p.nchunks * T * sizeof(uint32_t)) + tgs_align_up(T * sizeof(uint32_t)) +
+           tgs_align_up(sizeof(uint32_t));                // count matrix, column totals, number of live chunks
+}
+static uint32_t* live_chunks_of(const void* temp, int nchunks, int T) {
+    return (uint32_t*)((char*)temp + tgs_align_up((size_t)nchunks * T * sizeof(uint32_t)) + tgs_align_up((size_t)T * sizeof(uint32_t)));
 }
 
 // Phase 0: depth order of the Gaussians.
@@ -440,6 +463,7 @@ int tgs_bin_count(GeomView gv, int N, int Tx, int Ty, int row0, int row1, void* 
     const Plan p = make_plan(N, Tx, row1 - row0, row0 == 0 && row1 == Ty);      // bands over the rows this rank renders
     uint32_t* cnt = (uint32_t*)temp;
     uint32_t* totals = (uint32_t*)((char*)temp + tgs_align_up((size_t)p.nchunks * T * sizeof(uint32_t)));
+    uint32_t* live = live_chunks_of(temp, p.nchunks, T);
     const int t_begin = row0 * Tx, t_end = row1 * Tx;
     static bool attr_done[64] = {};
     int dev = 0;
@@ -454,13 +478,14 @@ int tgs_bin_count(GeomView gv, int N, int Tx, int Ty, int row0, int row1, void* 
     {
         TgsProfScope prof(TGS_STAGE_DUPLICATE, st);
         k_bin_count<<<dim3(p.nchunks, p.count.n), 256, (size_t)p.count.tiles * 4, st>>>(
-            N, p.chunk, gv.order, gv.tiles_touched, gv.rect, Tx, row0, row1, p.count.rows, T, cnt, gv.span_sorted);
+            N, p.chunk, gv.order, gv.depth_keys_sorted, gv.tiles_touched, gv.rect, Tx, row0, row1, p.count.rows, T, cnt,
+            gv.span_sorted, live);
         tgs_count_own(1);
         TGS_CUDA(cudaGetLastError());
     }
     {
         TgsProfScope prof(TGS_STAGE_SORT, st);
-        k_bin_prefix<<<(t_end - t_begin + 31) / 32, 256, 0, st>>>(p.nchunks, T, t_begin, t_end, cnt, totals);
+        k_bin_prefix<<<(t_end - t_begin + 31) / 32, 256, 0, st>>>(live, T, t_begin, t_end, cnt, totals);
         k_bin_ranges<<<1, 1024, 0, st>>>(T, t_begin, t_end, totals, ranges, count_out);
         tgs_count_own(2);
         TGS_CUDA(cudaGetLastError());
@@ -483,7 +508,7 @@ int tgs_bin_scatter_pack(GeomView gv, BinView bv, int N, int64_t count, int64_t 
         auto kern = whole ? k_bin_scatter<1> : k_bin_scatter<8>;
         kern<<<p.nchunks * p.scatter.n, 32 * ksub, smem, st>>>(
             N, p.chunk, p.scatter.n, gv.order, gv.span_sorted, Tx, row0, row1, p.scatter.rows, T, cnt, ranges,
-            (uint32_t)(cap > 0xFFFFFFFFll ? 0xFFFFFFFFll : cap), bv.vals_sorted);
+            live_chunks_of(temp, p.nchunks, T), (uint32_t)(cap > 0xFFFFFFFFll ? 0xFFFFFFFFll : cap), bv.vals_sorted);
         tgs_count_own(1);
         TGS_CUDA(cudaGetLastError());
     }

@@ -83,7 +83,8 @@ int run_step(Pool& pool, const TgsSettings* sh, const TgsGaussians* gh, const fl
     float* alpha = (float*)pool.get(P * 4);
     float* dcolor = (float*)pool.get(3 * P * 4);
     int32_t* radii = (int32_t*)pool.get((n ? n : 1) * 4);
-    float* sgrad = (float*)pool.get((n ? n : 1) * TGS_NGRAD * 4);
+    s.contrib_flags = 0;                  // one GPU: plain rows (the chain rule skips the all-zero ones)
+    float* sgrad = (float*)pool.get(n ? tgs_screen_grad_bytes(N, 0) : 64);
     float* scal = (float*)pool.get(16);   // [0..1] touch scale + counter, [2] photometric loss
     if (!color || !depth || !alpha || !dcolor || !radii || !sgrad || !scal) { tgs_set_error("cudaMallocAsync failed"); return TGS_ENOMEM; }
     TGS_CUDA(cudaMemsetAsync(scal, 0, 16, st));

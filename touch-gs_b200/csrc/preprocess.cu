@@ -7,6 +7,7 @@
 // a 48 B record + 24 B cov3D + 4 B tiles + 4 B radii + 8 B rect + 1 B clamp mask; backward reads the
 // parameters again plus 40 B screen gradients and writes 4*(11+3K)+12 B of gradients.
 #include "tgs_common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -214,9 +215,31 @@ struct PeerGather {
     int world;                                   // 0: single buffer (`sgrad`), no exchange
     const float* ptr[TGS_MAX_PEERS];             // peer r's [N,10] partial screen-gradient buffer
     int row0[TGS_MAX_PEERS], row1[TGS_MAX_PEERS];  // tile-row band rendered by rank r
+    size_t flag_off;                             // SKIP == 2: byte offset of the contributor bytes in every buffer
 };
+// 32 bytes that are 0 or 1 -> one bit each (byte k -> bit k)
+__device__ __forceinline__ unsigned flag_bits(uint4 lo, uint4 hi) {
+    const unsigned w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    unsigned m = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m |= (((w[k] & 0x01010101u) * 0x10204080u) >> 28) << (4 * k);
+    return m;
+}
 
-template <bool STAGE>
+// GATHER (multi-GPU): the remote rows are REQUESTED before anything else is read, so the NVLink round trip (a few
+// microseconds through the switch) runs under the HBM round trips of the camera, the staging and the parameter loads.
+// SKIP: a Gaussian whose screen-gradient row is exactly zero -- culled, off screen, or (the common case in a dense
+// scene: 86 % at c3) hidden behind the depth at which its tiles saturate, so that no pixel ever blended it -- has zero
+// parameter gradients: its 236 bytes of parameters and SH coefficients are not read and no chain rule is evaluated;
+// zeros are written.  What the warp stages (the whole 6 KB SH block when most lanes need it, else row by row, exactly
+// like the forward does for the Gaussians outside a rank's band) is decided
+//   SKIP = 1: from the row itself, which therefore comes first;
+//   SKIP = 2: from the CONTRIBUTOR BYTES BACKWARD::render wrote behind the rows (TgsSettings.contrib_flags): one
+//             coalesced byte per Gaussian instead of a 40-byte row -- and in the multi-GPU gather one 32-byte sector per
+//             (warp, peer) tells which of the peer's rows are worth a round trip at all;
+//   SKIP = 0: nothing is skipped.
+// (Exact zeros in give exact zeros out except for non-finite parameters, where 0 x inf would have produced NaN.)
+template <bool STAGE, bool GATHER, int SKIP>
 __global__ void __launch_bounds__(kBlock, 3)
 k_preprocess_bwd(int N, PeerGather pg, const TgsRecord* __restrict__ rec, const float* __restrict__ means, const float* __restrict__ scales,
                  const float* __restrict__ rots, const float* __restrict__ shs,
@@ -229,37 +252,119 @@ k_preprocess_bwd(int N, PeerGather pg, const TgsRecord* __restrict__ rec, const 
                  float* __restrict__ dscales, float* __restrict__ drots, float* __restrict__ dcov3D) {
     __shared__ CamMats cm;
     extern __shared__ __align__(16) float4 s_stage[];
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    const bool inN = i < N;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int first = blockIdx.x * kBlock + warp * 32;
+    int rad = 0;
+    float py = 0.0f;                                      // rec[i].a.y (0 when culled)
+    unsigned live = 1;                                    // SKIP == 2, single buffer: this Gaussian's contributor byte
+    uint4 fl_lo = make_uint4(0u, 0u, 0u, 0u), fl_hi = fl_lo;   // SKIP == 2, gather: lane r holds peer r's 32 bytes
+    float2 pre[TGS_NGRAD / 2];                            // the (first) screen-gradient row, in flight
+#pragma unroll
+    for (int k = 0; k < TGS_NGRAD / 2; ++k) pre[k] = make_float2(0.f, 0.f);
+    if (GATHER && SKIP == 2 && first < N && lane < pg.world) {
+        // the contributor bytes of this warp's 32 Gaussians on peer `lane`: one 32-byte sector over NVLink
+        const uint4* f = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(pg.ptr[lane]) + pg.flag_off + first);
+        fl_lo = f[0]; fl_hi = f[1];
+    }
+    if (inN) {
+        rad = __ldg(radii + i);
+        if (GATHER) {
+            // the second value that decides which peers are asked.  (The branch further down tests BOTH values with a
+            // bitwise &: otherwise ptxas sinks this load into the `rad > 0` branch and serialises the two round trips.)
+            py = __ldg(reinterpret_cast<const float*>(rec + i) + 1);
+        } else if (SKIP == 2) {
+            live = reinterpret_cast<const uint8_t*>(sgrad)[pg.flag_off + i];
+        } else {
+            // rows of culled Gaussians are zero (the buffer is zeroed before BACKWARD::render): read without waiting for `rad`
+            const float2* s2 = reinterpret_cast<const float2*>(sgrad + (size_t)TGS_NGRAD * i);
+#pragma unroll
+            for (int k = 0; k < TGS_NGRAD / 2; ++k) pre[k] = s2[k];
+        }
+    }
     load_cam(vm, pm, campos, &cm);
-    int i = blockIdx.x * kBlock + threadIdx.x;
     // STAGE (K = 16): the warp's SH block comes in through shared memory, each thread turns its row into dL/dSH in
     // place, and the block goes back out to `dshs` with coalesced stores
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float4* s_rows = STAGE ? s_stage + (size_t)warp * 32 * kShRowPad : nullptr;
-    const int first = blockIdx.x * kBlock + warp * 32;
-    if (STAGE && first < N) warp_stage_in(shs, first, N, s_rows, lane);
-    if (i < N) {
-    float dm[3] = {0.f, 0.f, 0.f}, dc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    float ds[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
+    unsigned rmask = 0;                                   // GATHER: the ranks that hold a partial row of this Gaussian
+    if (GATHER) {
+        if (inN && ((rad > 0) & (py > -3.0e38f))) {
+            int y0, y1;                                   // the Gaussian's tile rows in the FULL image (getRect, unclipped)
+            tgs_rect1(py, (float)rad, cam.Ty, y0, y1);
+            for (int r = 0; r < pg.world; ++r)
+                if (y0 < pg.row1[r] && y1 > pg.row0[r]) rmask |= 1u << r;
+        }
+        if (SKIP == 2 && first < N) {
+            // ... of which only those that blended it have anything but zeros to give
+            const unsigned mine = flag_bits(fl_lo, fl_hi);
+            for (int r = 0; r < pg.world; ++r) {
+                const unsigned m = __shfl_sync(0xffffffffu, mine, r);
+                if (!((m >> lane) & 1u)) rmask &= ~(1u << r);
+            }
+        }
+        if (rmask) {
+            const float2* s2 = reinterpret_cast<const float2*>(pg.ptr[__ffs(rmask) - 1] + (size_t)TGS_NGRAD * i);
+#pragma unroll
+            for (int k = 0; k < TGS_NGRAD / 2; ++k) pre[k] = s2[k];
+        }
+    }
+    const bool vis = inN && rad > 0;
+    bool need = vis;
+    if (SKIP == 2) {
+        need = vis && (GATHER ? rmask != 0 : live != 0);
+        if (!GATHER && need) {
+            const float2* s2 = reinterpret_cast<const float2*>(sgrad + (size_t)TGS_NGRAD * i);
+#pragma unroll
+            for (int k = 0; k < TGS_NGRAD / 2; ++k) pre[k] = s2[k];
+        }
+    }
+    if (STAGE && first < N) {
+        if (SKIP == 0) {
+            warp_stage_in(shs, first, N, s_rows, lane);
+        } else if (SKIP == 2) {                           // known before the rows arrive: the staging overlaps them
+            const unsigned m = __ballot_sync(0xffffffffu, need);
+            if (__popc(m) > 12) warp_stage_in(shs, first, N, s_rows, lane);
+            else if (m) warp_stage_rows(shs, first, s_rows, m, lane);
+        }
+    }
     float sg[TGS_NGRAD];
 #pragma unroll
     for (int k = 0; k < TGS_NGRAD; ++k) sg[k] = 0.0f;
-    bool vis = radii[i] > 0;
-    if (vis) {
-        if (pg.world == 0) {
-            const float2* s2 = reinterpret_cast<const float2*>(sgrad + (size_t)TGS_NGRAD * i);
+    if (need) {
+        if (GATHER) {
+            // ascending rank order, starting from 0.0f: bit-identical on every rank
+            if (rmask) {
 #pragma unroll
-            for (int k = 0; k < TGS_NGRAD / 2; ++k) { float2 v = s2[k]; sg[2 * k] = v.x; sg[2 * k + 1] = v.y; }
-        } else {
-            int y0, y1;                               // the Gaussian's tile rows in the FULL image (getRect, unclipped)
-            tgs_rect1(rec[i].a.y, (float)radii[i], cam.Ty, y0, y1);
-            for (int r = 0; r < pg.world; ++r) {
-                if (y0 < pg.row1[r] && y1 > pg.row0[r]) {
-                    const float2* s2 = reinterpret_cast<const float2*>(pg.ptr[r] + (size_t)TGS_NGRAD * i);
-#pragma unroll
-                    for (int k = 0; k < TGS_NGRAD / 2; ++k) { float2 v = s2[k]; sg[2 * k] += v.x; sg[2 * k + 1] += v.y; }
-                }
+                for (int k = 0; k < TGS_NGRAD / 2; ++k) { sg[2 * k] += pre[k].x; sg[2 * k + 1] += pre[k].y; }
+                rmask &= rmask - 1;
             }
+            while (rmask) {
+                const float2* s2 = reinterpret_cast<const float2*>(pg.ptr[__ffs(rmask) - 1] + (size_t)TGS_NGRAD * i);
+                rmask &= rmask - 1;
+#pragma unroll
+                for (int k = 0; k < TGS_NGRAD / 2; ++k) { float2 v = s2[k]; sg[2 * k] += v.x; sg[2 * k + 1] += v.y; }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < TGS_NGRAD / 2; ++k) { sg[2 * k] = pre[k].x; sg[2 * k + 1] = pre[k].y; }
         }
+    }
+    if (SKIP == 1) {
+        bool nz = false;
+#pragma unroll
+        for (int k = 0; k < TGS_NGRAD; ++k) nz |= sg[k] != 0.0f;          // NaN != 0: a poisoned row is not skipped
+        need = vis && nz;
+        if (STAGE && first < N) {
+            const unsigned m = __ballot_sync(0xffffffffu, need);
+            if (__popc(m) > 12) warp_stage_in(shs, first, N, s_rows, lane);
+            else if (m) warp_stage_rows(shs, first, s_rows, m, lane);
+        }
+    }
+    if (inN) {
+    float dm[3] = {0.f, 0.f, 0.f}, dc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float ds[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
+    if (need) {
         float x = means[3 * i], y = means[3 * i + 1], z = means[3 * i + 2];
         float cov[6];
 #pragma unroll
@@ -320,7 +425,7 @@ k_preprocess_bwd(int N, PeerGather pg, const TgsRecord* __restrict__ rec, const 
 #pragma unroll
         for (int k = 0; k < 6; ++k) dcov3D[6 * i + k] = dc[k];
     }
-    }   // i < N
+    }   // inN
     if (STAGE && first < N) warp_stage_out(dshs, first, N, s_rows, lane);
 }
 
@@ -343,7 +448,17 @@ static cudaError_t enable_stage_smem() {
     if (dev < 0 || dev >= 64 || done[dev]) return cudaSuccess;
     e = cudaFuncSetAttribute(k_preprocess<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShStageBytes);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_preprocess_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShStageBytes);
+    e = cudaFuncSetAttribute(k_preprocess_bwd<true, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShStageBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_preprocess_bwd<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShStageBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_preprocess_bwd<true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShStageBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_preprocess_bwd<true, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShStageBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_preprocess_bwd<true, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShStageBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_preprocess_bwd<true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kShStageBytes);
     if (e == cudaSuccess) done[dev] = true;
     return e;
 }
@@ -367,12 +482,13 @@ int tgs_launch_preprocess(const TgsCam& cam, const TgsSettings* s, const TgsGaus
 
 int tgs_launch_preprocess_bwd(const TgsCam& cam, const TgsSettings* s, const TgsGaussians* g,
                               GeomView gv, const int32_t* radii, const float* screen_grads,
-                              const float* const* peer_grads, const int32_t* peer_rows, int world,
+                              const float* const* peer_grads, const int32_t* peer_rows, int world, bool with_flags,
                               const TgsGrads* gr, cudaStream_t st) {
     int N = g->N;
     if (N == 0) return 0;
     PeerGather pg;
     pg.world = 0;
+    pg.flag_off = TGS_SCREEN_GRAD_FLAG_OFFSET(N);
     for (int r = 0; r < TGS_MAX_PEERS; ++r) { pg.ptr[r] = nullptr; pg.row0[r] = pg.row1[r] = 0; }
     if (world > 0) {
         pg.world = world;
@@ -381,7 +497,21 @@ int tgs_launch_preprocess_bwd(const TgsCam& cam, const TgsSettings* s, const Tgs
     TgsProfScope prof(TGS_STAGE_PREPROCESS_BWD, st);
     const bool stage = g->shs != nullptr && cam.K == 16;
     TGS_CUDA(enable_stage_smem());
-    auto kern = stage ? k_preprocess_bwd<true> : k_preprocess_bwd<false>;
+    // Which shortcut (see the kernel): contributor bytes when the buffers carry them; else the zero-row test for a single
+    // buffer, and nothing for a gather over plain rows (waiting for the remote rows before the SH block is staged costs more
+    // than it saves: 0.150 vs 0.138 ms on 2 GPUs).  TGS_ZERO_SKIP=0|1 overrides (experiments; 2 needs the bytes).
+    static int skip_env = -2;
+    if (skip_env == -2) {
+        const char* e = getenv("TGS_ZERO_SKIP");
+        skip_env = e ? atoi(e) : -1;
+        if (skip_env < -1 || skip_env > 1) skip_env = -1;
+    }
+    const bool gather = world > 0;
+    const int skip = skip_env >= 0 ? skip_env : (with_flags ? 2 : (gather ? 0 : 1));
+#define TGS_PICK(ST, GA) (skip == 2 ? k_preprocess_bwd<ST, GA, 2> : skip == 1 ? k_preprocess_bwd<ST, GA, 1> : k_preprocess_bwd<ST, GA, 0>)
+    auto kern = stage ? (gather ? TGS_PICK(true, true) : TGS_PICK(true, false))
+                      : (gather ? TGS_PICK(false, true) : TGS_PICK(false, false));
+#undef TGS_PICK
     kern<<<(N + kBlock - 1) / kBlock, kBlock, stage ? kShStageBytes : 0, st>>>(
         N, pg, gv.records, g->means3D, g->scales, g->rotations, g->shs, g->cov3D_precomp, s->viewmatrix,
         s->projmatrix, s->campos, cam, gv.cov3D, gv.clamped, radii, screen_grads, gr->dmeans2D,

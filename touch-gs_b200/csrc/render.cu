@@ -341,7 +341,8 @@ k_render_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ ids,
              const float* __restrict__ dL_dalpha, const float* __restrict__ t_target,
              const float* __restrict__ t_weight, const float* __restrict__ t_scale,
              const float* __restrict__ t_gscale, int t_mode,
-             int t_row0, int t_row1, float* __restrict__ residual, float* __restrict__ sgrad) {
+             int t_row0, int t_row1, float* __restrict__ residual, float* __restrict__ sgrad,
+             uint8_t* __restrict__ contrib) {
     __shared__ __align__(128) float4 sbuf_all[kBwdWarps][2][kBwdBatch * 3];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4 (*sbuf)[kBwdBatch * 3] = sbuf_all[warp];
@@ -554,6 +555,9 @@ k_render_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ ids,
                     float sum; int slot; bool ok;
                     warp_reduce_scatter10(v, lane, sum, slot, ok);
                     if (ok) atomicAdd(sgrad + (size_t)__float_as_int(a.w) * TGS_NGRAD + slot, sum);
+                    // contributor byte (TgsSettings.contrib_flags): some pixel blended this Gaussian, its row is live.
+                    // One idle lane of the reduction stores it; every writer stores the same value.
+                    if (contrib != nullptr && lane == 31) contrib[__float_as_int(a.w)] = 1;
                 }
             }
             __syncwarp();
@@ -635,7 +639,8 @@ int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, const TgsReco
 int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, const TgsRecord* gv_records, BinView bv, ImageView iv,
                           int64_t num_rendered,
                           const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
-                          const TgsTouch* touch, float* residual, float* screen_grads, cudaStream_t st) {
+                          const TgsTouch* touch, float* residual, float* screen_grads, uint8_t* contrib_flags,
+                          cudaStream_t st) {
     int nt = cam.Tx * (cam.row1 - cam.row0);
     if (nt <= 0) return 0;
     const float* tt = nullptr; const float* tw = nullptr; const float* ts = nullptr; const float* tg = nullptr;
@@ -668,7 +673,8 @@ int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, const TgsReco
     k_render_bwd<<<(unsigned)grid, kBwdThreads, 0, st>>>(iv.ranges, bv.vals_sorted, reinterpret_cast<const float4*>(gv_records), cam.W, cam.H, cam.Tx, cam.row0, s->bg,
                                      s->depth_normalize, cam.alpha_max, iv.final_T, iv.n_contrib, iv.depth_raw,
                                      iv.color_acc, bv.ckpt, bv.slot_tile, bv.ckpt_list, bv.work_counter, 2 * nt, dL_dcolor,
-                                     dL_ddepth, dL_dalpha, tt, tw, ts, tg, mode, tr0, tr1, residual, screen_grads);
+                                     dL_ddepth, dL_dalpha, tt, tw, ts, tg, mode, tr0, tr1, residual, screen_grads,
+                                     contrib_flags);
     tgs_count_own(1);
     TGS_KERNEL_CHECK(st, s->debug);
     return 0;

@@ -131,7 +131,7 @@ extern "C" int tgs_project_gaussians_backward(const TgsSettings* s, const TgsGau
     TgsGrads gr = *grads;
     gr.dshs = nullptr; gr.dcolors = nullptr;
     return tgs_launch_preprocess_bwd(cam, s, &gg, tgs_geom_view(saved->geom, g->N), radii, screen_grads, nullptr, nullptr, 0,
-                                     &gr, (cudaStream_t)stream);
+                                     false, &gr, (cudaStream_t)stream);
 }
 
 extern "C" int tgs_rasterize_screen_forward(const TgsSettings* s, int32_t N, const float* xys, const float* depths,
@@ -198,7 +198,7 @@ extern "C" int tgs_rasterize_screen_backward(const TgsSettings* s, int32_t N, co
     if (!saved->geom) { tgs_set_error("tgs_rasterize_screen_backward: saved geometry missing"); return TGS_ESTATE; }
     GeomView gvb = tgs_geom_view(saved->geom, N);
     return tgs_launch_render_bwd(cam, &s2, gvb.records, bv, iv, saved->num_rendered, dL_dcolor, dL_ddepth, dL_dalpha, nullptr, nullptr,
-                                 screen_grads, st);
+                                 screen_grads, nullptr, st);
 }
 
 extern "C" int tgs_spherical_harmonics(int32_t N, int32_t degree, int32_t K, const float* dirs, const float* coeffs,

@@ -86,10 +86,11 @@ size_t tgs_bin_temp_bytes(int N, int Tx, int Ty);
 // preprocess.cu
 int tgs_launch_preprocess(const TgsCam& cam, const TgsSettings* s, const TgsGaussians* g,
                           GeomView gv, int32_t* radii, cudaStream_t st);
-// world > 0: gather the partial screen gradients from `peer_grads[0..world)` (bands in peer_rows[2r], [2r+1])
+// world > 0: gather the partial screen gradients from `peer_grads[0..world)` (bands in peer_rows[2r], [2r+1]).
+// `with_flags`: the buffer(s) carry contributor bytes at TGS_SCREEN_GRAD_FLAG_OFFSET(N) (TgsSettings.contrib_flags)
 int tgs_launch_preprocess_bwd(const TgsCam& cam, const TgsSettings* s, const TgsGaussians* g,
                               GeomView gv, const int32_t* radii, const float* screen_grads,
-                              const float* const* peer_grads, const int32_t* peer_rows, int world,
+                              const float* const* peer_grads, const int32_t* peer_rows, int world, bool with_flags,
                               const TgsGrads* grads, cudaStream_t st);
 int tgs_launch_mark_visible(int N, const float* means, const float* vm, uint8_t* present, cudaStream_t st);
 // binning.cu
@@ -108,7 +109,8 @@ int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, const TgsReco
 int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, const TgsRecord* gv_records, BinView bv, ImageView iv,
                           int64_t num_rendered,
                           const float* dL_dcolor, const float* dL_ddepth, const float* dL_dalpha,
-                          const TgsTouch* touch, float* residual, float* screen_grads, cudaStream_t st);
+                          const TgsTouch* touch, float* residual, float* screen_grads, uint8_t* contrib_flags,
+                          cudaStream_t st);
 int tgs_launch_loss_scale(const float* target, int64_t P, float mult, float norm, float* out, cudaStream_t st);
 int tgs_launch_touch_loss_value(const float* residual, const float* weight, int64_t i0, int64_t i1, int mode,
                                 const float* scale, double* acc, float* out, cudaStream_t st);

@@ -117,6 +117,7 @@ Inputs make_inputs(const Tensor& bg, const Tensor& means3D, const Tensor& colors
     s.tile_row_begin = (int32_t)row0; s.tile_row_end = (int32_t)row1;
     s.depth_normalize = depth_normalize; s.rendered_hint = rendered_hint > 0 ? rendered_hint : 0;
     s.defer_count = (defer_count && rendered_hint > 0) ? 1 : 0;
+    s.contrib_flags = 0;
     s.viewmatrix = fp(in.view); s.projmatrix = fp(in.proj); s.campos = fp(in.campos); s.bg = fp(in.bg);
     TgsGaussians& g = in.g;
     g.N = (int32_t)N;
@@ -224,6 +225,11 @@ GradTuple grad_tuple(GradOut& o) {
     return std::make_tuple(o.dmeans2D, o.dcolors, o.dopacity, o.dmeans3D, o.dcov3D, o.dsh, o.dscales, o.drot);
 }
 
+// floats a screen-gradient buffer must hold: the [N,10] rows (+ the contributor bytes, TgsSettings.contrib_flags)
+int64_t screen_grad_floats(int64_t N, bool contrib_flags) {
+    return (int64_t)((tgs_screen_grad_bytes((int32_t)N, contrib_flags ? 1 : 0) + 3) / 4);
+}
+
 // BACKWARD::render half: zeroes and fills `screen_grads` [N,10] (caller-owned: it may be a peer-mapped buffer)
 void backward_render(const Tensor& bg, const Tensor& means3D, const Tensor& colors, const Tensor& opacity, const Tensor& scales,
                      const Tensor& rotations, double scale_modifier, const Tensor& cov3D_precomp, const Tensor& viewmatrix,
@@ -232,7 +238,8 @@ void backward_render(const Tensor& bg, const Tensor& means3D, const Tensor& colo
                      bool depth_normalize, const Tensor& geom, const Tensor& binning, const Tensor& img, int64_t num_rendered,
                      int64_t capacity, const Tensor& dL_dcolor, const OptT& dL_ddepth, const OptT& dL_dalpha,
                      const OptT& touch_depth, const OptT& touch_weight, int64_t loss_mode, const OptT& loss_scale,
-                     const OptT& grad_scale, int64_t touch_row_begin, int64_t touch_row_end, Tensor screen_grads) {
+                     const OptT& grad_scale, int64_t touch_row_begin, int64_t touch_row_end, Tensor screen_grads,
+                     bool contrib_flags) {
     Inputs in = make_inputs(bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
                             projmatrix, tanfovx, tanfovy, H, W, sh, degree, campos, false, debug, tile_row_begin,
                             tile_row_end, depth_normalize, 0);
@@ -244,8 +251,10 @@ void backward_render(const Tensor& bg, const Tensor& means3D, const Tensor& colo
     if (dL_ddepth.has_value() && dL_ddepth->defined()) gd = f32(dL_ddepth->reshape({H, W}), "grad_depth", {H, W}, dev);
     if (dL_dalpha.has_value() && dL_dalpha->defined()) ga = f32(dL_dalpha->reshape({H, W}), "grad_alpha", {H, W}, dev);
     Touch th = make_touch(touch_depth, touch_weight, loss_mode, loss_scale, grad_scale, touch_row_begin, touch_row_end, H, W, dev);
+    in.s.contrib_flags = contrib_flags ? 1 : 0;
     TORCH_CHECK(screen_grads.defined() && screen_grads.is_contiguous() && screen_grads.scalar_type() == at::kFloat &&
-                screen_grads.device() == dev && screen_grads.numel() >= N * 10, "screen_grads must be a contiguous float32 [N,10] buffer on ", dev);
+                screen_grads.device() == dev && screen_grads.numel() >= screen_grad_floats(N, contrib_flags),
+                "screen_grads must be a contiguous float32 buffer of screen_grad_floats(N, contrib_flags) elements on ", dev);
     TgsSaved saved = make_saved(geom, binning, img, num_rendered, capacity);
     check_rc(tgs_backward_render(&in.s, &in.g, &saved, gc.data_ptr<float>(), fp(gd), fp(ga), th.on ? &th.t : nullptr, nullptr,
                                  N > 0 ? screen_grads.data_ptr<float>() : nullptr, cur_stream(dev)), "tgs_backward_render");
@@ -258,7 +267,7 @@ GradTuple backward_preprocess(const Tensor& means3D, const Tensor& radii, const 
                               const Tensor& viewmatrix, const Tensor& projmatrix, double tanfovx, double tanfovy, int64_t H,
                               int64_t W, const Tensor& sh, int64_t degree, const Tensor& campos, bool debug, const Tensor& geom,
                               const OptT& screen_grads, const std::vector<int64_t>& peer_ptrs,
-                              const std::vector<int64_t>& peer_rows) {
+                              const std::vector<int64_t>& peer_rows, bool contrib_flags) {
     Tensor bg = at::zeros({3}, means3D.options());
     Inputs in = make_inputs(bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix,
                             tanfovx, tanfovy, H, W, sh, degree, campos, false, debug, 0, 0, true, 0);
@@ -271,10 +280,11 @@ GradTuple backward_preprocess(const Tensor& means3D, const Tensor& radii, const 
     TgsSaved saved{};
     TORCH_CHECK(geom.defined() && geom.is_cuda(), "saved geometry buffer missing");
     saved.geom = geom.data_ptr();
+    in.s.contrib_flags = contrib_flags ? 1 : 0;
     if (peer_ptrs.empty()) {
         TORCH_CHECK(screen_grads.has_value() && screen_grads->defined(), "screen_grads required");
         Tensor sg = f32(screen_grads->reshape({-1}), "screen_grads", {-1}, dev);
-        TORCH_CHECK(sg.numel() >= N * 10, "screen_grads must hold [N,10] floats");
+        TORCH_CHECK(sg.numel() >= screen_grad_floats(N, contrib_flags), "screen_grads must hold screen_grad_floats(N, contrib_flags) floats");
         check_rc(tgs_backward_preprocess(&in.s, &in.g, &saved, rd.data_ptr<int32_t>(), fp(sg), &go.g, cur_stream(dev)),
                  "tgs_backward_preprocess");
     } else {
@@ -321,6 +331,8 @@ GradTuple rasterize_gaussians_backward(const Tensor& bg, const Tensor& means3D, 
     Touch th = make_touch(touch_depth, touch_weight, loss_mode, loss_scale, grad_scale, touch_row_begin, touch_row_end, H, W, dev);
     TgsSaved saved = make_saved(geom, binning, img, num_rendered, capacity);
     GradOut go = make_grads(in);
+    // plain rows: on one GPU the chain rule finds the Gaussians no pixel blended from the zero rows themselves, which is
+    // cheaper than having BACKWARD::render write contributor bytes (they pay off in the multi-GPU gather)
     Tensor sgrad = at::empty({N > 0 ? N : 1, 10}, at::TensorOptions().dtype(at::kFloat).device(dev));
     check_rc(tgs_backward(&in.s, &in.g, &saved, rd.data_ptr<int32_t>(), gc.data_ptr<float>(), fp(gd), fp(ga),
                           th.on ? &th.t : nullptr, nullptr, sgrad.data_ptr<float>(), &go.g, cur_stream(dev)), "tgs_backward");
@@ -411,6 +423,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("rasterize_gaussians_backward", &rasterize_gaussians_backward);
     m.def("backward_render", &backward_render);
     m.def("backward_preprocess", &backward_preprocess);
+    m.def("screen_grad_floats", &screen_grad_floats);
     m.def("mark_visible", &mark_visible);
     m.def("resolve_count", [](int64_t ticket, int64_t capacity) {
         int64_t n = 0;

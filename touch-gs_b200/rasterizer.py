@@ -316,22 +316,26 @@ def _backward_ext(ctx, g_color, g_depth, g_alpha, g_tloss):
             sgrad, peer_ptrs, peer_handle = peer.acquire(N)         # this rank's peer-mapped buffer of the step
         else:
             sgrad = torch.empty((max(N, 1), L.NGRAD), dtype=torch.float32, device=dev)
+        # peer buffers carry contributor bytes behind the rows (the gather asks a peer only for rows it wrote); a buffer
+        # that goes through an all-reduce must be plain [N,10]
+        flags = peer is not None
         ext.backward_render(rs.bg, means3D, colors, opacities, scales, rots, *cam, H, W, sh, int(rs.sh_degree), rs.campos,
                             bool(rs.debug), r0, r1, bool(opt.depth_normalize), geom, binning, image, ctx.num_rendered,
                             ctx.capacity, g_color, g_depth, g_alpha, touch_depth if mode != L.LOSS_NONE else None, touch_weight,
-                            mode, ctx.tscale, gs, tr[0], tr[1], sgrad)
+                            mode, ctx.tscale, gs, tr[0], tr[1], sgrad, flags)
         pre = (means3D, radii, colors, opacities, scales, rots, *cam, H, W, sh, int(rs.sh_degree), rs.campos, bool(rs.debug), geom)
         if peer is not None:
             # FUSED exchange: wait until every rank has finished BACKWARD::render, then the chain-rule
             # kernel gathers each Gaussian's partial sums straight from the owning peers' buffers over NVLink
             peer_handle.barrier(channel=0)
-            grads = ext.backward_preprocess(*pre, None, [int(p or 0) for p in peer_ptrs], [int(v) for b in peer.bands for v in b])
+            grads = ext.backward_preprocess(*pre, None, [int(p or 0) for p in peer_ptrs], [int(v) for b in peer.bands for v in b],
+                                            True)
         else:
             # the ONE exchange step of the multi-GPU path: sum the compact [N,10] screen-space gradients of all
             # tile-row bands, NCCL over NVLink
             import torch.distributed as dist
             dist.all_reduce(sgrad, op=dist.ReduceOp.SUM, group=opt.process_group)
-            grads = ext.backward_preprocess(*pre, sgrad, [], [])
+            grads = ext.backward_preprocess(*pre, sgrad, [], [], False)
     dmeans2D, dcol, dopac, dmeans3D, dcov, dsh, dsc, drot = grads
     has_sh, has_col, has_sr, has_cov = ctx.has
     out = (dmeans3D, dmeans2D, dsh if has_sh else None, dcol if has_col else None, dopac.reshape(ctx.opacity_shape),
@@ -514,8 +518,12 @@ class _RasterizeGaussians(torch.autograd.Function):
                 peer = None
             if peer is not None:
                 sgrad, peer_ptrs, peer_handle = peer.acquire(N)     # this rank's peer-mapped buffer of the step
+                s.contrib_flags = 1                                 # ... which carries contributor bytes behind the rows
             else:
+                # plain rows: required when the buffer is all-reduced, and on one GPU the chain rule finds the
+                # non-contributors from the zero rows themselves (cheaper than writing the bytes in BACKWARD::render)
                 sgrad = torch.empty((max(N, 1), L.NGRAD), dtype=torch.float32, device=dev)
+                s.contrib_flags = 0
             L.check(lib.tgs_backward_render(C.byref(s), C.byref(g), C.byref(saved), _ptr(g_color), _ptr(g_depth),
                                             _ptr(g_alpha), None if touch is None else C.byref(touch), None,
                                             _ptr(sgrad), _stream_ptr(dev)), "tgs_backward_render")

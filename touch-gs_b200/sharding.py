@@ -1,12 +1,15 @@
 """Tile-row sharding of one camera's image across the GPUs of a box.
 
 Every rank holds a full replica of the Gaussians and renders a contiguous band of tile rows; the
-backward produces *partial* screen-space gradients [N,10] which are summed with ONE all-reduce per
-step (NCCL over NVLink on GPUs, gloo in the CPU tests).  No other data-path collective exists.
+backward produces *partial* screen-space gradients [N,10]; the chain-rule kernel gathers them straight from the
+peers' buffers over NVLink (PeerScreenGrads), or they are summed with ONE all-reduce per step (NCCL on GPUs, gloo in
+the CPU tests).  No other data-path collective exists.
 """
 from __future__ import annotations
 
 from typing import List, Sequence, Tuple
+
+from . import _lib
 
 TILE = 16
 
@@ -100,7 +103,8 @@ class PeerScreenGrads:
         except Exception:  # noqa: BLE001
             pass
         for _ in range(2):
-            t = symm.empty(self.capacity * n_grad, dtype=torch.float32, device=device)
+            # rows + contributor bytes (TgsSettings.contrib_flags): the gather asks a peer only for the rows it wrote
+            t = symm.empty(max(_lib.screen_grad_floats(self.capacity, True), 1), dtype=torch.float32, device=device)
             h = symm.rendezvous(t, name)
             ptrs = [int(p) for p in h.buffer_ptrs]
             self.bufs.append(t)
@@ -110,12 +114,13 @@ class PeerScreenGrads:
         self.bands = None
 
     def acquire(self, N: int):
-        """-> (this step's [N,10] buffer of THIS rank, ctypes array of all ranks' pointers, barrier handle)"""
+        """-> (this step's buffer of THIS rank: screen_grad_floats(N, True) floats = [N,10] rows + contributor bytes,
+        ctypes array of all ranks' pointers, barrier handle)"""
         if N > self.capacity:
             raise ValueError(f"PeerScreenGrads capacity {self.capacity} < {N} Gaussians")
         i = self.k & 1
         self.k += 1
-        return self.bufs[i][: N * self.n_grad].view(N, self.n_grad), self.ptr_arrays[i], self.handles[i]
+        return self.bufs[i][: _lib.screen_grad_floats(N, True)], self.ptr_arrays[i], self.handles[i]
 
     def band_array(self):
         import ctypes as C
