@@ -329,6 +329,9 @@ constexpr int kBwdBatch = 64;
 constexpr int kPix = 4;
 constexpr int kSeg = 256;                       // == kBatch: the forward checkpoints once per staged batch
 
+// FLAGS: also write the contributor bytes (TgsSettings.contrib_flags).  A template parameter, not a run-time test: the
+// kernel is bound by instruction issue, and even a never-taken branch on a NULL pointer cost 2.5 % (0.554 -> 0.568 ms).
+template <bool FLAGS>
 __global__ void __launch_bounds__(kBwdThreads, 5)
 k_render_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ ids, const float4* __restrict__ table,
              int W, int H, int Tx,
@@ -557,7 +560,7 @@ k_render_bwd(const uint2* __restrict__ ranges, const uint32_t* __restrict__ ids,
                     if (ok) atomicAdd(sgrad + (size_t)__float_as_int(a.w) * TGS_NGRAD + slot, sum);
                     // contributor byte (TgsSettings.contrib_flags): some pixel blended this Gaussian, its row is live.
                     // One idle lane of the reduction stores it; every writer stores the same value.
-                    if (contrib != nullptr && lane == 31) contrib[__float_as_int(a.w)] = 1;
+                    if (FLAGS && lane == 31) contrib[__float_as_int(a.w)] = 1;
                 }
             }
             __syncwarp();
@@ -662,7 +665,7 @@ int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, const TgsReco
     int dev = 0;
     TGS_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && ctas_per_sm[dev] == 0) {
-        TGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[dev], k_render_bwd, kBwdThreads, 0));
+        TGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[dev], k_render_bwd<false>, kBwdThreads, 0));
         TGS_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
     }
     const int cps = (dev >= 0 && dev < 64 && ctas_per_sm[dev] > 0) ? ctas_per_sm[dev] : 4;
@@ -670,7 +673,8 @@ int tgs_launch_render_bwd(const TgsCam& cam, const TgsSettings* s, const TgsReco
     int64_t grid = (units + kBwdWarps - 1) / kBwdWarps;
     if (grid > (int64_t)cps * sms) grid = (int64_t)cps * sms;        // persistent: one resident wave
     TGS_CUDA(cudaMemsetAsync(bv.work_counter, 0, sizeof(uint32_t), st));
-    k_render_bwd<<<(unsigned)grid, kBwdThreads, 0, st>>>(iv.ranges, bv.vals_sorted, reinterpret_cast<const float4*>(gv_records), cam.W, cam.H, cam.Tx, cam.row0, s->bg,
+    auto kern = contrib_flags ? k_render_bwd<true> : k_render_bwd<false>;
+    kern<<<(unsigned)grid, kBwdThreads, 0, st>>>(iv.ranges, bv.vals_sorted, reinterpret_cast<const float4*>(gv_records), cam.W, cam.H, cam.Tx, cam.row0, s->bg,
                                      s->depth_normalize, cam.alpha_max, iv.final_T, iv.n_contrib, iv.depth_raw,
                                      iv.color_acc, bv.ckpt, bv.slot_tile, bv.ckpt_list, bv.work_counter, 2 * nt, dL_dcolor,
                                      dL_ddepth, dL_dalpha, tt, tw, ts, tg, mode, tr0, tr1, residual, screen_grads,
