@@ -4,6 +4,9 @@ gather kernel.  cuda:0 plays rank 0 (renders tile rows [0, 34) into its [N,10] b
 rows straight out of cuda:1's memory over NVLink (peer access enabled through torch).  c3 scene, camera 0.
 
     ncu --metrics nvlrx__bytes.sum,nvltx__bytes.sum,gpu__time_duration.sum -k regex:k_preprocess_bwd python profiles/peer_gather_ncu.py
+
+FLAGS=1 (default): the buffers carry the contributor bytes (TgsSettings.contrib_flags) and the gather asks rank 1 only for the
+rows it flagged; FLAGS=0: plain [N,10] rows, every row of a Gaussian whose span touches rank 1's band is read.
 """
 import ctypes as C
 import os
@@ -25,6 +28,8 @@ H, W, deg, N = cfg["H"], cfg["W"], 3, cfg["N"]
 sc = T.synth.make_scene(N, deg, cfg["smin"], cfg["smax"], 0)
 cam = T.synth.orbit_cameras(W, H, 8, 3.0, 0)[0]
 bands = T.sharding.even_bands(H, 2)
+FLAGS = os.environ.get("FLAGS", "1") != "0"
+NF = L.screen_grad_floats(N, FLAGS)
 g = torch.Generator().manual_seed(0)
 grgb_cpu = torch.rand(3, H, W, generator=g) / (3 * H * W)
 state = []
@@ -46,7 +51,8 @@ for r in (0, 1):
         L.check(lib.tgs_forward(C.byref(st), C.byref(gs), scratch.cb, None, p(out[0]), p(out[1]), p(out[2]), p(out[3]), None, None,
                                 C.byref(saved), stream), "fwd")
         scratch.disarm()
-        sg = torch.zeros(N, 10, device=dev)
+        st.contrib_flags = 1 if FLAGS else 0
+        sg = torch.zeros(NF, device=dev)
         grgb = grgb_cpu.to(dev)
         L.check(lib.tgs_backward_render(C.byref(st), C.byref(gs), C.byref(saved), p(grgb), None, None, None, None, p(sg), stream), "bwd")
         torch.cuda.synchronize(dev)
@@ -74,13 +80,15 @@ with torch.cuda.device(0):
                                                    C.c_void_p(s0["radii"].data_ptr()), ptrs, rows, 2, C.byref(grads), stream), "gather")
     torch.cuda.synchronize(dev)
     # reference: summed buffers through the plain entry point
-    total = state[0]["sg"] + state[1]["sg"].to(dev)
+    rows0, rows1 = state[0]["sg"][: 10 * N].view(N, 10), state[1]["sg"][: 10 * N].view(N, 10)
+    total = rows0 + rows1.to(dev)
+    s0["st"].contrib_flags = 0                       # the summed buffer is plain [N,10]
     gr2 = {k: torch.empty_like(v) for k, v in gr.items()}
     grads2 = L.TgsGrads(**{k: v.data_ptr() for k, v in gr2.items()})
     L.check(lib.tgs_backward_preprocess(C.byref(s0["st"]), C.byref(s0["gs"]), C.byref(s0["saved"]), C.c_void_p(s0["radii"].data_ptr()),
                                         C.c_void_p(total.data_ptr()), C.byref(grads2), stream), "plain")
     torch.cuda.synchronize(dev)
     same = all(torch.equal(gr[k], gr2[k]) for k in gr)
-    remote_rows = int((state[1]["sg"].abs().sum(1) > 0).sum())
-    print(f"peer gather over NVLink == summed buffers: {same}; rank 1 holds {remote_rows} non-zero rows "
+    remote_rows = int((rows1.abs().sum(1) > 0).sum())
+    print(f"contrib_flags={int(FLAGS)}: peer gather over NVLink == summed buffers: {same}; rank 1 holds {remote_rows} non-zero rows "
           f"({remote_rows * 40 / 1e6:.1f} MB of 40-byte rows)")
