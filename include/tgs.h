@@ -38,7 +38,7 @@ extern "C" {
 
 /* which scratch buffer an allocation is for (the three opaque byte buffers of SURVEY §8b) */
 #define TGS_BUF_GEOM    0   /* per-Gaussian state, lives fwd -> bwd */
-#define TGS_BUF_BINNING 1   /* per-instance state (sorted list, packed records) */
+#define TGS_BUF_BINNING 1   /* per-instance state (the sorted id list, checkpoints of the segmented backward) */
 #define TGS_BUF_IMAGE   2   /* per-pixel state (final_T, n_contrib, raw depth) */
 #define TGS_BUF_TEMP    3   /* temporaries not needed by backward */
 

@@ -42,6 +42,13 @@ step(tile_rows=(2, 6))                    # a band of a tile-row shard (8-warp s
 for binding in ("ctypes", "ext"):
     T._lib.use_binding(binding)
     step()
+# the multi-GPU gather, one device playing 2 and 8 ranks, with the contributor bytes behind the rows and without
+# (k_render_bwd<FLAGS>, k_preprocess_bwd<STAGE, GATHER, SKIP = 0 | 2>); the same function the GPU test suite runs
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import test_fullsize_parity as tfp  # noqa: E402
+for world, flags in ((2, True), (8, True), (2, False)):
+    tfp.test_emulated_peer_gather_is_bit_identical_to_summed_buffers(world, flags)
+torch.cuda.synchronize()
 # trainer step with refine (activations, SSIM loss, Adam, densify)
 raw = [sc.means3D, sc.shs, torch.logit(sc.opacities.reshape(-1).clamp(1e-4, 1 - 1e-4)), torch.log(sc.scales), sc.rotations]
 tr = T.TouchGSTrainer(*[t.to(dev) for t in raw], T.TrainConfig(sh_degree=3, refine_every=2, warmup_length=0, sh_degree_interval=0,

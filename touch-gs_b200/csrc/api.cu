@@ -275,12 +275,12 @@ extern "C" int tgs_forward(const TgsSettings* s, const TgsGaussians* g, tgs_allo
     void* temp = nullptr;
     uint32_t* hp = pinned_word();
     if (!hp) { tgs_set_error("cudaHostAlloc failed"); return TGS_ENOMEM; }
-    auto tail = [&](int64_t count, int64_t capacity, bool spec) -> int {      // scatter + pack + render for `capacity` slots
+    auto tail = [&](int64_t count, int64_t capacity, bool spec) -> int {      // scatter + render for `capacity` slots
         TgsBinningLayout bl; tgs_binning_layout(capacity, &bl);
         binning = alloc(user, TGS_BUF_BINNING, bl.total);
         if (!binning) { tgs_set_error("allocator returned NULL"); return TGS_ENOMEM; }
         BinView bv = tgs_bin_view(binning, capacity);
-        int r = tgs_bin_scatter_pack(gv, bv, N, count, capacity, spec, cam.Tx, cam.Ty, cam.row0, cam.row1, temp, iv.ranges, iv.count, st); if (r) return r;
+        int r = tgs_bin_scatter(gv, bv, N, count, capacity, spec, cam.Tx, cam.Ty, cam.row0, cam.row1, temp, iv.ranges, iv.count, st); if (r) return r;
         if (s->debug) TGS_CUDA(cudaStreamSynchronize(st));
         return tgs_launch_render_fwd(cam, s, gv.records, bv, iv, capacity, out_color, out_depth, out_alpha, touch_target, residual_out, st);
     };
@@ -307,7 +307,7 @@ extern "C" int tgs_forward(const TgsSettings* s, const TgsGaussians* g, tgs_allo
         }
         TGS_CUDA(cudaMemcpyAsync(hp, iv.count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         if (s->rendered_hint > 0) {
-            // SPECULATIVE: enqueue scatter + pack + render for `hint` slots, THEN wait for the count (event recorded
+            // SPECULATIVE: enqueue scatter + render for `hint` slots, THEN wait for the count (event recorded
             // right after the count kernels: the GPU keeps working on the speculative tail while the host wakes up)
             cudaEvent_t ev = count_event();
             if (!ev) { tgs_set_error("cudaEventCreate failed"); return TGS_ENOMEM; }

@@ -29,9 +29,9 @@
 //
 // Replaces: emission of (tile id, Gaussian id) pairs + two CUB onesweep passes over I pairs + boundary detection
 // (0.048 + 0.190 ms at c3, and 12 B/instance of key/value traffic per pass) by three small kernels over N Gaussians.
-// Roofline: HBM.  Algorithmic bytes per instance: key/val write 12, sort 24, range detect 8,
-// record gather 48 + write 48; what actually moves: 4 B (id) written once + the 96 B of the record pack, plus
-// 12 B x chunks x T of count-matrix traffic (0.1 GB at c3).
+// Roofline: HBM.  Algorithmic bytes per instance: key/val write 12, sort 24, range detect 8; what
+// actually moves: 4 B (the id) written once per instance, plus 8 B x live chunks x T of count-matrix traffic (0.06 GB
+// at c3) -- the compositing kernels gather the 48-byte records by id, no per-instance copy of them exists.
 #include "tgs_common.cuh"
 #include <cub/cub.cuh>
 #include <cstdlib>
@@ -494,7 +494,7 @@ int tgs_bin_count(GeomView gv, int N, int Tx, int Ty, int row0, int row1, void* 
 }
 
 // Phase 3.  `cap` = instances the binning buffer holds (speculative mode: positions beyond it are not written).
-int tgs_bin_scatter_pack(GeomView gv, BinView bv, int N, int64_t count, int64_t cap, bool speculative, int Tx, int Ty,
+int tgs_bin_scatter(GeomView gv, BinView bv, int N, int64_t count, int64_t cap, bool speculative, int Tx, int Ty,
                          int row0, int row1, const void* temp, const uint2* ranges, const uint32_t* count_dev, cudaStream_t st) {
     if (count == 0 || N == 0 || row1 <= row0) return 0;
     const int T = Tx * Ty;

@@ -24,6 +24,7 @@
 // Roofline: HBM.  Algorithmic bytes: forward 48 B/instance + 24 B/pixel written;
 // backward 48 B/instance read + 40 B/instance accumulated + 32 B/pixel.
 #include "tgs_common.cuh"
+#include <cstdlib>
 #include "render_math.cuh"
 
 namespace {
@@ -147,6 +148,13 @@ __device__ __forceinline__ bool patch_may_touch(const float4 a, const float4 q, 
 constexpr int kIdRing = 3;
 constexpr int kIdSlots = kBatch + 4;             // a 16-byte aligned window around 256 ids
 
+// kMbar = true (product): the arrival of a batch's records is tracked by an mbarrier -- every thread posts
+// cp.async.mbarrier.arrive.noinc behind its three copies, the consumers wait on the barrier's phase (PTX: when the wait
+// returns, all cp.async operations the participating threads requested before their cp.async.mbarrier.arrive are performed
+// and visible).  kMbar = false (TGS_FWD_RECORD_SYNC=waitgroup, diagnostics): the classic cp.async.wait_group + block
+// barrier instead, one more __syncthreads per batch.  compute-sanitizer's racecheck does not model the mbarrier form and
+// reports the record stage as racing; with the wait_group form it is clean (profiles/r04i_sanitizer_racecheck*.log).
+template <bool kMbar>
 __global__ void __launch_bounds__(256)
 k_render_fwd(const uint2* __restrict__ ranges, uint32_t cap, const uint32_t* __restrict__ ids,
              const float4* __restrict__ table, int W, int H, int Tx,
@@ -195,7 +203,8 @@ k_render_fwd(const uint2* __restrict__ ranges, uint32_t cap, const uint32_t* __r
             cp_async16(dst, src); cp_async16(dst + 1, src + 1); cp_async16(dst + 2, src + 2);
         }
         // arrive on the stage's mbarrier when THIS thread's copies have landed (immediately if it issued none)
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[b & 1])) : "memory");
+        if (kMbar) asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[b & 1])) : "memory");
+        else cp_async_commit();
     };
     if (tid == 0) { for (int b = 0; b < kIdRing && b < nb; ++b) issue_ids(b); }
     if (nb > 0) gather(0);
@@ -206,7 +215,12 @@ k_render_fwd(const uint2* __restrict__ ranges, uint32_t cap, const uint32_t* __r
     bool done = !pm.inside;
     int b = 0;
     for (; b < nb; ++b) {
-        mbar_wait(&full[b & 1], (uint32_t)((b >> 1) & 1));               // all 256 threads' copies of batch b have landed
+        if (kMbar) {
+            mbar_wait(&full[b & 1], (uint32_t)((b >> 1) & 1));           // all 256 threads' copies of batch b have landed
+        } else {
+            if (b + 1 < nb) cp_async_wait<1>(); else cp_async_wait<0>(); // this thread's copies of batch b ...
+            __syncthreads();                                             // ... and everybody else's
+        }
         const float4* s = sbuf[b & 1];
         const int cnt = min(kBatch, len - b * kBatch);
         for (int c0 = 0; c0 < cnt; c0 += 32) {
@@ -629,7 +643,13 @@ int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, const TgsReco
     if (nt <= 0) return 0;
     TgsProfScope prof(TGS_STAGE_RENDER_FWD, st);
     TGS_CUDA(cudaMemsetAsync(bv.work_counter, 0, 2 * sizeof(uint32_t), st));
-    k_render_fwd<<<nt, 256, 0, st>>>(iv.ranges, (uint32_t)(capacity > 0xFFFFFFFFll ? 0xFFFFFFFFll : capacity), bv.vals_sorted,
+    static int waitgroup = -1;
+    if (waitgroup < 0) {
+        const char* e = getenv("TGS_FWD_RECORD_SYNC");
+        waitgroup = (e && e[0] == 'w') ? 1 : 0;
+    }
+    auto kern = waitgroup ? k_render_fwd<false> : k_render_fwd<true>;
+    kern<<<nt, 256, 0, st>>>(iv.ranges, (uint32_t)(capacity > 0xFFFFFFFFll ? 0xFFFFFFFFll : capacity), bv.vals_sorted,
                                      reinterpret_cast<const float4*>(gv_records), cam.W, cam.H, cam.Tx, cam.row0, s->bg,
                                      s->depth_normalize, cam.alpha_max, out_color, out_depth, out_alpha, iv.final_T,
                                      iv.n_contrib, iv.depth_raw, iv.color_acc, bv.ckpt, bv.slot_tile, bv.ckpt_list,

@@ -175,7 +175,7 @@ extern "C" int tgs_rasterize_screen_forward(const TgsSettings* s, int32_t N, con
     void* binning = alloc(user, TGS_BUF_BINNING, bl.total);
     if (!binning) { tgs_set_error("allocator returned NULL"); return TGS_ENOMEM; }
     BinView bv = tgs_bin_view(binning, I);
-    rc = tgs_bin_scatter_pack(gv, bv, N, I, I, false, cam.Tx, cam.Ty, cam.row0, cam.row1, temp, iv.ranges, iv.count, st); if (rc) return rc;
+    rc = tgs_bin_scatter(gv, bv, N, I, I, false, cam.Tx, cam.Ty, cam.row0, cam.row1, temp, iv.ranges, iv.count, st); if (rc) return rc;
     TgsSettings s2 = *s;
     s2.depth_normalize = 0;
     rc = tgs_launch_render_fwd(cam, &s2, gv.records, bv, iv, I, out_color, out_depth, out_alpha, nullptr, nullptr, st); if (rc) return rc;

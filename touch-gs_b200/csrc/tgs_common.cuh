@@ -1,5 +1,5 @@
-// tgs_common.cuh -- shared declarations of libtgs.so (layouts of the saved buffers, the packed
-// per-instance record, error plumbing, kernel-launcher prototypes between translation units).
+// tgs_common.cuh -- shared declarations of libtgs.so (layouts of the saved buffers, the 48-byte
+// per-Gaussian record, error plumbing, kernel-launcher prototypes between translation units).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -98,9 +98,9 @@ int tgs_depth_order(GeomView gv, int N, cudaStream_t st);
 // count matrix + per-tile prefixes + ranges + instance count (device: count_out[0] = I, count_out[1] = overflow flag)
 int tgs_bin_count(GeomView gv, int N, int Tx, int Ty, int row0, int row1, void* temp, uint2* ranges, uint32_t* count_out,
                   cudaStream_t st);
-// `cap` = instances the binning buffer holds; `count` = instances to pack (== I in exact mode, == cap in speculative
+// `cap` = instances the binning buffer holds; `count` = instances to place (== I in exact mode, == cap in speculative
 // mode, where the real count is read on the device from count_dev)
-int tgs_bin_scatter_pack(GeomView gv, BinView bv, int N, int64_t count, int64_t cap, bool speculative, int Tx, int Ty,
+int tgs_bin_scatter(GeomView gv, BinView bv, int N, int64_t count, int64_t cap, bool speculative, int Tx, int Ty,
                          int row0, int row1, const void* temp, const uint2* ranges, const uint32_t* count_dev, cudaStream_t st);
 // render.cu
 int tgs_launch_render_fwd(const TgsCam& cam, const TgsSettings* s, const TgsRecord* gv_records, BinView bv, ImageView iv,
