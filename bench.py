@@ -88,6 +88,7 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    PERIOD_MS = 25          # the default timed region is ~150 ms: several samples land inside it
 
     def __init__(self, index: int):
         self.index, self.lines, self.proc = index, [], None
@@ -95,7 +96,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", str(self.PERIOD_MS), "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -112,7 +113,7 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return
-        time.sleep(0.12)
+        time.sleep(0.04)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -123,10 +124,10 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         window = "timed region"
-        rows = [l for t, l in self.lines if t_begin <= t <= t_end + 0.11]
+        rows = [l for t, l in self.lines if t_begin <= t <= t_end + 0.03]
         if not rows:        # timed region shorter than the polling period: use everything since warm-up began
-            rows = [l for t, l in self.lines if t_warm <= t <= t_end + 0.11]
-            window = "warm-up + timed region (timed region shorter than the 100 ms polling period)"
+            rows = [l for t, l in self.lines if t_warm <= t <= t_end + 0.03]
+            window = "warm-up + timed region (timed region shorter than the polling period)"
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in rows:
