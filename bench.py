@@ -88,7 +88,9 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
-    PERIOD_MS = 25          # the default timed region is ~150 ms: several samples land inside it
+    # one GPU: the default timed region is ~150 ms, several 25 ms samples land inside it.  Under torchrun every rank runs
+    # its own sampler: keep the 100 ms period there so that 8 pollers do not compete for the driver
+    PERIOD_MS = 25 if int(os.environ.get("WORLD_SIZE", "1")) == 1 else 100
 
     def __init__(self, index: int):
         self.index, self.lines, self.proc = index, [], None
@@ -113,7 +115,7 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return
-        time.sleep(0.04)
+        time.sleep(self.PERIOD_MS * 1.2e-3)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -124,9 +126,9 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         window = "timed region"
-        rows = [l for t, l in self.lines if t_begin <= t <= t_end + 0.03]
+        rows = [l for t, l in self.lines if t_begin <= t <= t_end + self.PERIOD_MS * 1.1e-3]
         if not rows:        # timed region shorter than the polling period: use everything since warm-up began
-            rows = [l for t, l in self.lines if t_warm <= t <= t_end + 0.03]
+            rows = [l for t, l in self.lines if t_warm <= t <= t_end + self.PERIOD_MS * 1.1e-3]
             window = "warm-up + timed region (timed region shorter than the polling period)"
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
