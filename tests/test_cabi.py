@@ -206,3 +206,12 @@ def test_gsplat_style_surface_rejects_cpu_tensors(tgs_lib):
     with pytest.raises(RuntimeError, match="CUDA-only"):
         G.spherical_harmonics(3, z(4, 3), z(4, 16, 3))
     assert G.PIXEL_CENTER_OFFSET == 0.5 and G.ALPHA_MAX == 0.999
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No silent fallback: without the built CUDA library the product refuses to load (and says how to build it)."""
+    L = T._lib
+    monkeypatch.setattr(L, "_lib", None)
+    monkeypatch.setattr(L, "LIB_PATH", str(tmp_path / "libtgs.so"))
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        L.load()
