@@ -35,6 +35,29 @@ def test_balanced_bands():
     assert sharding.band_pixel_rows((34, 68), 1080) == (544, 1080)
 
 
+def test_balanced_bands_properties():
+    """Property test (hypothesis): the bands are a contiguous partition of the tile rows, nobody is left without a row
+    while rows remain, and no band carries more than its share plus one row's worth of work."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(st.one_of(st.just(0.0), st.floats(0.0, 1e6, allow_nan=False, allow_infinity=False),
+                              st.integers(0, 5).map(float)), min_size=1, max_size=140),
+           st.sampled_from([1, 2, 3, 4, 8]))
+    def check(work, g):
+        b = sharding.balanced_bands(work, g)
+        Ty = len(work)
+        assert len(b) == g and b[0][0] == 0 and b[-1][1] == Ty
+        assert all(b[i][1] == b[i + 1][0] for i in range(g - 1)) and all(e >= s for s, e in b)
+        if Ty >= g:
+            assert all(e > s for s, e in b)
+            total = sum(work)
+            if total > 0:
+                assert max(sum(work[s:e]) for s, e in b) <= total / g + max(work) + 1e-6 * total
+
+    check()
+
+
 def _leaf_pre(pre):
     """Detach the per-Gaussian screen-space quantities into leaves (depth is an ancestor of conic in
     the full graph, so *partial* derivatives -- what tgs_backward_render emits -- need a cut graph)."""
