@@ -209,3 +209,28 @@ def test_oracle_convention_switches_are_self_consistent():
     lo = O.render_tiles(one, b1, S0).alpha.max()
     hi = O.render_tiles(one, b1, O.OracleSettings(**base, alpha_max=0.999)).alpha.max()
     assert abs(float(lo) - 0.99) < 1e-3 and float(hi) > 0.995
+
+
+def test_unblended_gaussians_have_exactly_zero_gradients():
+    """The premise of k_preprocess_bwd's zero-row shortcut and of the contributor bytes of the multi-GPU gather, checked on
+    the spec side: a Gaussian that no pixel blends (culled, off screen, or hidden behind the depth at which its tiles
+    saturate) receives EXACTLY zero gradients on every parameter -- its whole screen-space row is zero, not just small."""
+    torch.manual_seed(0)
+    sc = synth.make_scene(400, 3, 0.05, 0.5, seed=7)             # large, mostly opaque splats: deep layers are hidden
+    sc = sc._replace(opacities=torch.full_like(sc.opacities, 0.97))
+    cam = synth.look_at_camera(64, 48, (0.2, 0.1, -3.0))
+    tgt = torch.full((48, 64), 2.8)
+    touch = dict(touch_depth=tgt, touch_weight=torch.ones(48, 64), depth_loss="l1", depth_loss_mult=0.2)
+    out, ins = _run(sc, cam, torch.float64, touch=touch)
+    out.pre.rgb.retain_grad()
+    g = torch.Generator().manual_seed(5)
+    grgb = torch.rand(3, 48, 64, generator=g).double() + 0.1      # strictly positive: every blended splat gets colour gradient
+    ((out.color * grgb).sum() + (out.depth * 0.3).sum() + (out.alpha * 0.2).sum() + out.touch_loss).backward()
+    blended = (out.pre.rgb.grad != 0).any(1)
+    visible = out.radii > 0
+    assert int(blended.sum()) > 20 and int((visible & ~blended).sum()) > 20, "scene must have both blended and hidden splats"
+    assert not bool((blended & ~visible).any())
+    for name, t in zip(("means3D", "scales", "rotations", "opacities", "shs"), ins):
+        gr = t.grad.reshape(t.shape[0], -1)
+        assert bool((gr[~blended] == 0).all()), f"{name}: a Gaussian no pixel blended has a non-zero gradient"
+        assert bool((gr[blended] != 0).any(1).all()), f"{name}: a blended Gaussian with an all-zero gradient"
